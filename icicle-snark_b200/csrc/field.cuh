@@ -1,0 +1,327 @@
+// BN254 prime-field arithmetic (Fr and Fq) on 8x32-bit limbs, Montgomery form, R = 2^256.
+//
+// Replaces the reference's Field<CONFIG> (Karatsuba + Barrett):
+//   /root/reference/icicle/include/icicle/math/modular_arithmetic.h:337-352,383-388,490-494,556-564,601-631
+//   /root/reference/icicle/backend/cuda/include/cuda_math.h:299-346,491-526
+// Values held in Fp<> are ALWAYS Montgomery residues, fully reduced to [0, p).  The reference's
+// boundary format (standard form, 8xu32 LE) is produced/consumed by to_mont()/from_mont().
+//
+// Device path: generated PTX carry chains (field_asm.inc.h, see tools/gen_field_asm.py).
+// Host path (used by the host-side helpers bn254_add/ecadd/..., never as a fallback for
+// device work): portable 64-bit CIOS.
+#pragma once
+#include <cstdint>
+#include <cstring>
+
+#include "field_asm.inc.h"
+
+#if defined(__CUDACC__)
+#define B200_HD __host__ __device__ __forceinline__
+#define B200_D __device__ __forceinline__
+#else
+#define B200_HD inline
+#define B200_D inline
+#endif
+
+namespace b200 {
+
+  struct FrCfg {
+    // r = 0x30644e72e131a029b85045b68181585d2833e84879b9709143e1f593f0000001  (bn254_scalar.h:9-10)
+    static constexpr B200_HD uint32_t P(int i)
+    {
+      constexpr uint32_t t[8] = {0xf0000001, 0x43e1f593, 0x79b97091, 0x2833e848,
+                                      0x8181585d, 0xb85045b6, 0xe131a029, 0x30644e72};
+      return t[i];
+    }
+    static constexpr B200_HD uint32_t ONE(int i)
+    {
+      constexpr uint32_t t[8] = {0x4ffffffb, 0xac96341c, 0x9f60cd29, 0x36fc7695,
+                                        0x7879462e, 0x666ea36f, 0x9a07df2f, 0x0e0a77c1};
+      return t[i];
+    } // 2^256 mod r
+    static constexpr B200_HD uint32_t R2(int i)
+    {
+      constexpr uint32_t t[8] = {0xae216da7, 0x1bb8e645, 0xe35c59e3, 0x53fe3ab1,
+                                       0x53bb8085, 0x8c49833d, 0x7f4e44a5, 0x0216d0b1};
+      return t[i];
+    } // 2^512 mod r
+    static constexpr uint32_t INV = 0xefffffff; // -r^-1 mod 2^32
+#ifdef __CUDA_ARCH__
+    static B200_D void redc(uint32_t (&X)[8], uint32_t (&Y)[8]) { ptx::redc_fr(X, Y); }
+    static B200_D uint32_t subp(uint32_t (&T)[8], const uint32_t (&R)[8]) { return ptx::subp_fr(T, R); }
+    static B200_D void addp_masked(uint32_t (&R)[8], uint32_t mk) { ptx::addp_masked_fr(R, mk); }
+#endif
+  };
+
+  struct FqCfg {
+    // q = 0x30644e72e131a029b85045b68181585d97816a916871ca8d3c208c16d87cfd47  (bn254_base.h:8-9)
+    static constexpr B200_HD uint32_t P(int i)
+    {
+      constexpr uint32_t t[8] = {0xd87cfd47, 0x3c208c16, 0x6871ca8d, 0x97816a91,
+                                      0x8181585d, 0xb85045b6, 0xe131a029, 0x30644e72};
+      return t[i];
+    }
+    static constexpr B200_HD uint32_t ONE(int i)
+    {
+      constexpr uint32_t t[8] = {0xc58f0d9d, 0xd35d438d, 0xf5c70b3d, 0x0a78eb28,
+                                        0x7879462c, 0x666ea36f, 0x9a07df2f, 0x0e0a77c1};
+      return t[i];
+    } // 2^256 mod q
+    static constexpr B200_HD uint32_t R2(int i)
+    {
+      constexpr uint32_t t[8] = {0x538afa89, 0xf32cfc5b, 0xd44501fb, 0xb5e71911,
+                                       0x0a417ff6, 0x47ab1eff, 0xcab8351f, 0x06d89f71};
+      return t[i];
+    } // 2^512 mod q
+    static constexpr uint32_t INV = 0xe4866389; // -q^-1 mod 2^32
+#ifdef __CUDA_ARCH__
+    static B200_D void redc(uint32_t (&X)[8], uint32_t (&Y)[8]) { ptx::redc_fq(X, Y); }
+    static B200_D uint32_t subp(uint32_t (&T)[8], const uint32_t (&R)[8]) { return ptx::subp_fq(T, R); }
+    static B200_D void addp_masked(uint32_t (&R)[8], uint32_t mk) { ptx::addp_masked_fq(R, mk); }
+#endif
+  };
+
+  template <class Cfg>
+  struct alignas(16) Fp {
+    uint32_t v[8];
+
+    static B200_HD Fp zero()
+    {
+      Fp r;
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        r.v[i] = 0;
+      return r;
+    }
+    static B200_HD Fp one()
+    {
+      Fp r;
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        r.v[i] = Cfg::ONE(i);
+      return r;
+    }
+    static B200_HD Fp r2()
+    {
+      Fp r;
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        r.v[i] = Cfg::R2(i);
+      return r;
+    }
+    static B200_HD Fp raw_one()
+    {
+      Fp r = zero();
+      r.v[0] = 1;
+      return r;
+    }
+
+    B200_HD bool is_zero() const
+    {
+      uint32_t o = 0;
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        o |= v[i];
+      return o == 0;
+    }
+    friend B200_HD bool operator==(const Fp& a, const Fp& b)
+    {
+      uint32_t o = 0;
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        o |= a.v[i] ^ b.v[i];
+      return o == 0;
+    }
+    friend B200_HD bool operator!=(const Fp& a, const Fp& b) { return !(a == b); }
+
+    // ------------------------------------------------------------------ add / sub / neg
+    friend B200_HD Fp operator+(const Fp& a, const Fp& b)
+    {
+      Fp r;
+#ifdef __CUDA_ARCH__
+      uint32_t s[8], t[8];
+      ptx::add8(s, a.v, b.v); // a+b < 2p < 2^255: no carry out
+      uint32_t bw = Cfg::subp(t, s);
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        r.v[i] = bw ? s[i] : t[i];
+#else
+      uint32_t s[8], t[8];
+      uint64_t c = 0;
+      for (int i = 0; i < 8; ++i) {
+        c += (uint64_t)a.v[i] + b.v[i];
+        s[i] = (uint32_t)c;
+        c >>= 32;
+      }
+      int64_t bw = 0;
+      for (int i = 0; i < 8; ++i) {
+        int64_t d = (int64_t)s[i] - Cfg::P(i) + bw;
+        t[i] = (uint32_t)d;
+        bw = d >> 32;
+      }
+      for (int i = 0; i < 8; ++i)
+        r.v[i] = bw ? s[i] : t[i];
+#endif
+      return r;
+    }
+
+    friend B200_HD Fp operator-(const Fp& a, const Fp& b)
+    {
+      Fp r;
+#ifdef __CUDA_ARCH__
+      uint32_t bw = ptx::sub8(r.v, a.v, b.v);
+      Cfg::addp_masked(r.v, bw);
+#else
+      int64_t bw = 0;
+      for (int i = 0; i < 8; ++i) {
+        int64_t d = (int64_t)a.v[i] - b.v[i] + bw;
+        r.v[i] = (uint32_t)d;
+        bw = d >> 32;
+      }
+      if (bw) {
+        uint64_t c = 0;
+        for (int i = 0; i < 8; ++i) {
+          c += (uint64_t)r.v[i] + Cfg::P(i);
+          r.v[i] = (uint32_t)c;
+          c >>= 32;
+        }
+      }
+#endif
+      return r;
+    }
+
+    B200_HD Fp neg() const { return zero() - *this; }
+    B200_HD Fp dbl() const { return *this + *this; }
+
+    // ------------------------------------------------------------------ Montgomery product
+    friend B200_HD Fp operator*(const Fp& a, const Fp& b)
+    {
+      Fp r;
+#ifdef __CUDA_ARCH__
+      uint32_t X[8], Y[8];
+      ptx::mul_first(X, Y, a.v, b.v[0]);
+      Cfg::redc(X, Y);
+      ptx::mul_acc(Y, X, a.v, b.v[1]);
+      Cfg::redc(Y, X);
+      ptx::mul_acc(X, Y, a.v, b.v[2]);
+      Cfg::redc(X, Y);
+      ptx::mul_acc(Y, X, a.v, b.v[3]);
+      Cfg::redc(Y, X);
+      ptx::mul_acc(X, Y, a.v, b.v[4]);
+      Cfg::redc(X, Y);
+      ptx::mul_acc(Y, X, a.v, b.v[5]);
+      Cfg::redc(Y, X);
+      ptx::mul_acc(X, Y, a.v, b.v[6]);
+      Cfg::redc(X, Y);
+      ptx::mul_acc(Y, X, a.v, b.v[7]);
+      Cfg::redc(Y, X);
+      uint32_t s[8], t[8];
+      ptx::merge(s, Y, X); // last row's aligned accumulator is Y
+      uint32_t bw = Cfg::subp(t, s);
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        r.v[i] = bw ? s[i] : t[i];
+#else
+      uint32_t t[10] = {0};
+      for (int i = 0; i < 8; ++i) {
+        uint64_t c = 0;
+        for (int j = 0; j < 8; ++j) {
+          c += (uint64_t)a.v[j] * b.v[i] + t[j];
+          t[j] = (uint32_t)c;
+          c >>= 32;
+        }
+        c += t[8];
+        t[8] = (uint32_t)c;
+        t[9] = (uint32_t)(c >> 32);
+        uint32_t m = t[0] * Cfg::INV;
+        c = ((uint64_t)m * Cfg::P(0) + t[0]) >> 32;
+        for (int j = 1; j < 8; ++j) {
+          c += (uint64_t)m * Cfg::P(j) + t[j];
+          t[j - 1] = (uint32_t)c;
+          c >>= 32;
+        }
+        c += t[8];
+        t[7] = (uint32_t)c;
+        t[8] = t[9] + (uint32_t)(c >> 32);
+      }
+      uint32_t u[8];
+      int64_t bw = 0;
+      for (int i = 0; i < 8; ++i) {
+        int64_t d = (int64_t)t[i] - Cfg::P(i) + bw;
+        u[i] = (uint32_t)d;
+        bw = d >> 32;
+      }
+      bool ge = (t[8] != 0) || (bw == 0);
+      for (int i = 0; i < 8; ++i)
+        r.v[i] = ge ? u[i] : t[i];
+#endif
+      return r;
+    }
+
+    B200_HD Fp sqr() const { return *this * *this; }
+
+    // standard form (as at the reference's API boundary) <-> Montgomery
+    static B200_HD Fp to_mont(const Fp& std_form) { return std_form * r2(); }
+    static B200_HD Fp from_mont(const Fp& m) { return m * raw_one(); }
+
+    // a^(p-2); inverse(0) == 0 like the reference (modular_arithmetic.h:603)
+    B200_HD Fp inverse() const
+    {
+      // exponent p-2, scanned MSB first
+      uint32_t e[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        e[i] = Cfg::P(i);
+      e[0] -= 2; // P[0] >= 2 for both fields, no borrow
+      Fp acc = one();
+      for (int i = 7; i >= 0; --i) {
+        for (int b = 31; b >= 0; --b) {
+          acc = acc.sqr();
+          if ((e[i] >> b) & 1) acc = acc * *this;
+        }
+      }
+      return acc;
+    }
+  };
+
+  typedef Fp<FrCfg> Fr;
+  typedef Fp<FqCfg> Fq;
+
+  // ---------------------------------------------------------------------------------------------
+  // Fq2 = Fq[u]/(u^2+1)  (nonresidue -1: /root/reference/icicle/include/icicle/fields/snark_fields/bn254_base.h:67-71;
+  // reference product: /root/reference/icicle/include/icicle/fields/complex_extension.h:192-219)
+  struct alignas(16) Fq2 {
+    Fq c0, c1;
+    static B200_HD Fq2 zero() { return {Fq::zero(), Fq::zero()}; }
+    static B200_HD Fq2 one() { return {Fq::one(), Fq::zero()}; }
+    B200_HD bool is_zero() const { return c0.is_zero() && c1.is_zero(); }
+    friend B200_HD bool operator==(const Fq2& a, const Fq2& b) { return a.c0 == b.c0 && a.c1 == b.c1; }
+    friend B200_HD bool operator!=(const Fq2& a, const Fq2& b) { return !(a == b); }
+    friend B200_HD Fq2 operator+(const Fq2& a, const Fq2& b) { return {a.c0 + b.c0, a.c1 + b.c1}; }
+    friend B200_HD Fq2 operator-(const Fq2& a, const Fq2& b) { return {a.c0 - b.c0, a.c1 - b.c1}; }
+    B200_HD Fq2 neg() const { return {c0.neg(), c1.neg()}; }
+    B200_HD Fq2 dbl() const { return {c0.dbl(), c1.dbl()}; }
+    friend B200_HD Fq2 operator*(const Fq2& a, const Fq2& b)
+    {
+      // Karatsuba: 3 base-field products
+      Fq t0 = a.c0 * b.c0;
+      Fq t1 = a.c1 * b.c1;
+      Fq t2 = (a.c0 + a.c1) * (b.c0 + b.c1);
+      return {t0 - t1, t2 - t0 - t1};
+    }
+    B200_HD Fq2 sqr() const
+    {
+      // (c0+c1)(c0-c1), 2 c0 c1 : 2 base-field products
+      Fq s = c0 + c1, d = c0 - c1, m = c0 * c1;
+      return {s * d, m.dbl()};
+    }
+    static B200_HD Fq2 to_mont(const Fq2& a) { return {Fq::to_mont(a.c0), Fq::to_mont(a.c1)}; }
+    static B200_HD Fq2 from_mont(const Fq2& a) { return {Fq::from_mont(a.c0), Fq::from_mont(a.c1)}; }
+    B200_HD Fq2 inverse() const
+    {
+      Fq n = (c0.sqr() + c1.sqr()).inverse();
+      return {c0 * n, (c1 * n).neg()};
+    }
+  };
+
+} // namespace b200

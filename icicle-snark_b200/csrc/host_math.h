@@ -1,0 +1,48 @@
+// Host-side group helpers shared by host_math.cu (FFI scalar helpers) and the prover epilogue.
+#pragma once
+#include <random>
+
+#include "curve.cuh"
+
+namespace b200 {
+
+  template <class F>
+  inline Projective<F> proj_to_mont(const Projective<F>& p)
+  {
+    return {F::to_mont(p.x), F::to_mont(p.y), F::to_mont(p.z)};
+  }
+  template <class F>
+  inline Projective<F> proj_from_mont(const Projective<F>& p)
+  {
+    return {F::from_mont(p.x), F::from_mont(p.y), F::from_mont(p.z)};
+  }
+  template <class F>
+  inline Affine<F> affine_to_mont(const Affine<F>& p)
+  {
+    return {F::to_mont(p.x), F::to_mont(p.y)};
+  }
+  template <class F>
+  inline Affine<F> affine_from_mont(const Affine<F>& p)
+  {
+    return {F::from_mont(p.x), F::from_mont(p.y)};
+  }
+
+  // k*P, k in STANDARD form; plain MSB-first double-and-add (host, a handful of calls per proof)
+  template <class F>
+  inline XYZZ<F> host_scalar_mul(const XYZZ<F>& p, const Fr& k_std)
+  {
+    XYZZ<F> acc = XYZZ<F>::inf();
+    for (int i = 7; i >= 0; --i) {
+      for (int b = 31; b >= 0; --b) {
+        acc = acc.dbl();
+        if ((k_std.v[i] >> b) & 1) acc.add(p);
+      }
+    }
+    return acc;
+  }
+
+  G1Affine g1_generator_mont();
+  G2Affine g2_generator_mont();
+  Fr host_random_fr(std::mt19937_64& rng); // standard form, uniform in [0, r)
+
+} // namespace b200
