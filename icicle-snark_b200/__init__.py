@@ -1,0 +1,40 @@
+"""icicle-snark_b200: B200-native Groth16 proving hot path behind icicle-snark's API.
+
+Python host-side mirror of the reference's Rust layers for the hot path (the container has no
+Rust toolchain; see INTEGRATION.md for the Rust-side binding):
+
+  bindings.IcicleLib   <-> wrappers/rust/icicle-{runtime,core,curves/icicle-bn254}  (op-level C ABI)
+  prover.groth16_prove <-> src/lib.rs:33-61, src/cache.rs CacheManager               (fused C ABI)
+
+All arithmetic is in csrc/ (hand-written sm_100a CUDA behind lib/libicicle_b200.so).  There is no
+CPU fallback: loading fails loudly if the library has not been built.
+
+The directory name contains a hyphen (it mirrors the reference's repo name), so import it through
+`load_package()` in __graft_entry__.py / tests/conftest.py, which registers it as `icicle_snark_b200`.
+"""
+import os
+import subprocess
+
+from .bindings import *  # noqa: F401,F403
+from .bindings import IcicleLib
+
+PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(PKG_DIR, "lib", "libicicle_b200.so")
+
+_lib = None
+
+
+def build(jobs=8, verbose=False):
+    """Compile csrc/*.cu for sm_100a into lib/libicicle_b200.so (nvcc; no GPU needed)."""
+    r = subprocess.run(["make", "-C", PKG_DIR, f"-j{jobs}"], capture_output=not verbose, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("building libicicle_b200.so failed:\n" + (r.stdout or "") + (r.stderr or ""))
+    return LIB_PATH
+
+
+def lib() -> IcicleLib:
+    """The product library (process-wide singleton)."""
+    global _lib
+    if _lib is None:
+        _lib = IcicleLib(LIB_PATH)
+    return _lib

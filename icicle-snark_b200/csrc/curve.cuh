@@ -39,6 +39,16 @@ namespace b200 {
     }
     B200_HD XYZZ neg() const { return {x, y.neg(), zz, zzz}; }
 
+    // out-of-line twins for the exceptional branches of madd/add (P == Q is rare): keeps the hot
+    // accumulate loop's register and instruction footprint to the generic case
+#if defined(__CUDACC__)
+    static __host__ __device__ __noinline__ XYZZ dbl_affine_cold(const Affine<F>& p) { return dbl_affine(p); }
+    __host__ __device__ __noinline__ XYZZ dbl_cold() const { return dbl(); }
+#else
+    static XYZZ dbl_affine_cold(const Affine<F>& p) { return dbl_affine(p); }
+    XYZZ dbl_cold() const { return dbl(); }
+#endif
+
     // 2*(affine p), p != inf            (mdbl-2008-s-1)
     static B200_HD XYZZ dbl_affine(const Affine<F>& p)
     {
@@ -86,7 +96,7 @@ namespace b200 {
       F r = s2 - y;
       if (pp_.is_zero()) {
         if (r.is_zero())
-          *this = dbl_affine(p);
+          *this = dbl_affine_cold(p);
         else
           *this = inf();
         return;
@@ -117,7 +127,7 @@ namespace b200 {
       F r = s2 - s1;
       if (pp_.is_zero()) {
         if (r.is_zero())
-          *this = dbl();
+          *this = dbl_cold();
         else
           *this = inf();
         return;

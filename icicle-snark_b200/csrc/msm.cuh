@@ -5,18 +5,17 @@
 //
 //   reference                                   here
 //   ---------                                   ----
-//   unsigned c-bit digits (:166-203)            signed digits (add-constant recoding): half the buckets
+//   unsigned c-bit digits (:166-203)            signed digits by add-constant recoding: half the buckets,
+//                                               every window independent (no carry between windows)
 //   CUB radix sort of all 32 key bits + RLE     counting sort: histogram in the digit pass, one scan,
-//   + scan + second sort by bucket size         window-major scatter (L2-resident write window)
-//   one thread per bucket, serial (:223-255)    one thread per fixed-length SEGMENT of the sorted entry
-//   + large-bucket side path (:666-765)         list: perfectly balanced for any scalar distribution;
-//                                               buckets cut by a segment border are stitched by a
-//                                               fix-up pass (short spans: 1 thread, long spans: 1 CTA)
+//   + scan + second sort by bucket size         window-major scatter (L2-resident write window); bucket
+//                                               work items counting-sorted by length so a warp's lanes finish together
+//   one thread per bucket, serial (:223-255)    one thread per work item = (bucket, <= T entries); buckets longer
+//   + large-bucket side path (:666-765)         than T (skewed scalars) are cut into items whose partial sums
+//                                               are folded by a second small kernel
 //   projective RCB adds (12M+)                  XYZZ buckets, affine bases: 8M+2S per accumulate step
-//   log-halving reduction (:846-942)            chunked running sums + per-set tree, Horner over sets
-//   precompute_factor (:29-43)                  same idea; factor == #windows collapses all windows
-//                                               into ONE bucket set (no doublings at all) — affordable
-//                                               because the zkey bases live in 180 GB of HBM
+//   log-halving reduction (:846-942)            chunked running sums, one CTA tree per window, Horner over windows
+//   precompute_factor (:29-43)                  same table layout out[i*f+j] = 2^(shift*j) P_i
 #pragma once
 #include "common.cuh"
 #include "curve.cuh"
@@ -25,37 +24,34 @@
 namespace b200 {
 
   struct MsmPlan {
-    int n;           // points
-    int c;           // window bits
-    int windows;     // W = ceil((bitsize+1)/c)
-    int factor;      // precompute factor f (tables of 2^(c*sets*j) * P)
-    int sets;        // bucket sets = ceil(W/f)
-    int buckets;     // per set: 2^(c-1)
-    int keys;        // sets * buckets
-    int seg;         // entries per accumulate thread
-    uint32_t hconst[9]; // recoding constant H = sum_w (2^(c-1)-1) 2^(cw), 288 bits
-    size_t max_entries() const { return (size_t)n * windows; }
-    size_t max_segments() const { return (max_entries() + seg - 1) / seg; }
+    int n;        // scalars
+    int c;        // window bits
+    int windows;  // digits per scalar: ceil((bitsize+2)/c)
+    int factor;   // precompute factor f
+    int sets;     // bucket sets after precompute folding: ceil(windows/f)
+    int bpw;      // buckets per set: 2^(c-1)
+    int nbuckets; // sets * bpw
+    int item_cap; // T: max entries per accumulate work item
+    uint32_t hconst[9]; // recoding constant H = sum_w 2^(c-1) 2^(cw), 288 bits
+    size_t entries() const { return (size_t)n * windows; }
   };
 
   MsmPlan make_msm_plan(int n, int c_req, int bitsize, int factor, bool g2);
 
-  // Enqueue one MSM on `st`.  All pointers are DEVICE pointers; `bases_mont` holds factor*n affine
-  // points in Montgomery form laid out table-major ([j][i]); `out_xyzz` receives the result (Montgomery).
+  // Enqueue one MSM on `st`.  All pointers are DEVICE pointers; `bases_mont` holds n*factor affine
+  // points in Montgomery form ([i*f + j] = 2^(shift*j) P_i); `out_std` receives the result in the
+  // reference's boundary layout (homogeneous projective, standard form).
   template <class F>
   eIcicleError msm_enqueue(
-    const MsmPlan& plan, const Fr* scalars, bool scalars_mont, const Affine<F>* bases_mont, XYZZ<F>* out_xyzz,
+    const MsmPlan& plan, const Fr* scalars, bool scalars_mont, const Affine<F>* bases_mont, Projective<F>* out_std,
     cudaStream_t st);
 
-  // out[j][i] = 2^(shift*j) * in[i], affine Montgomery in and out
+  // out[i*f + j] = 2^(shift*j) * in[i]; in: affine (standard or Montgomery), out: affine Montgomery or standard
   template <class F>
-  eIcicleError precompute_enqueue(const Affine<F>* in, int n, int factor, int shift, Affine<F>* out, cudaStream_t st);
+  eIcicleError precompute_enqueue(
+    const Affine<F>* in, bool in_mont, int n, int factor, int shift, Affine<F>* out, bool out_mont, cudaStream_t st);
 
-  // XYZZ (Montgomery) -> reference projective layout, standard form
-  template <class F>
-  eIcicleError xyzz_to_projective_enqueue(const XYZZ<F>* in, int count, Projective<F>* out_std, cudaStream_t st);
-
-  // number of kernel launches the last msm_enqueue issued (bench.py's gpu_launches claim)
-  int msm_last_launch_count();
+  // kernel launches issued by this library since load (bench.py's gpu_launches claim)
+  extern unsigned long long g_launches;
 
 } // namespace b200

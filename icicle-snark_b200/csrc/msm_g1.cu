@@ -1,0 +1,66 @@
+// BN254 G1 MSM instantiation + plan selection + the bn254_msm / bn254_msm_precompute_bases symbols
+// (/root/reference/icicle/src/msm.cpp:12-16,45-49).
+#include "msm_impl.cuh"
+
+namespace b200 {
+
+  unsigned long long g_launches = 0;
+
+  MsmPlan make_msm_plan(int n, int c_req, int bitsize, int factor, bool g2)
+  {
+    MsmPlan p;
+    p.n = n;
+    int c = c_req;
+    if (c <= 0) {
+      // window width: ~log2(n) - 5 keeps accumulate work (n * windows adds) well above the
+      // bucket-reduction work (2 * sets * 2^(c-1) full adds); the reference uses log2(n) - 4
+      // with unsigned digits (cuda_msm.cuh:45-48), i.e. the same bucket count.
+      int lg = 0;
+      while ((1ll << lg) < n) ++lg;
+      c = lg - 5;
+      if (g2) c -= 1;
+    }
+    if (c < 2) c = 2;
+    if (c > 22) c = 22;
+    p.c = c;
+    p.windows = (bitsize + 2 + c - 1) / c;
+    p.factor = factor < 1 ? 1 : factor;
+    if (p.factor > p.windows) p.factor = p.windows;
+    p.sets = (p.windows + p.factor - 1) / p.factor;
+    p.bpw = 1 << (c - 1);
+    p.nbuckets = p.sets * p.bpw;
+    p.item_cap = 256;
+    // H = sum_w 2^(c-1) * 2^(c*w)
+    for (int i = 0; i < 9; ++i)
+      p.hconst[i] = 0;
+    for (int w = 0; w < p.windows; ++w) {
+      int bit = w * c + c - 1;
+      p.hconst[bit >> 5] |= 1u << (bit & 31);
+    }
+    return p;
+  }
+
+  template eIcicleError msm_enqueue<Fq>(const MsmPlan&, const Fr*, bool, const Affine<Fq>*, Projective<Fq>*, cudaStream_t);
+  template eIcicleError precompute_enqueue<Fq>(const Affine<Fq>*, bool, int, int, int, Affine<Fq>*, bool, cudaStream_t);
+
+} // namespace b200
+
+using namespace b200;
+
+extern "C" {
+
+eIcicleError bn254_msm(
+  const bn254_scalar_t* scalars, const bn254_affine_t* bases, int msm_size, const MSMConfig* config, bn254_projective_t* results)
+{
+  return msm_api<Fq>(scalars, bases, msm_size, config, results, false);
+}
+
+eIcicleError bn254_msm_precompute_bases(
+  const bn254_affine_t* input_bases, int bases_size, const MSMConfig* config, bn254_affine_t* output_bases)
+{
+  return precompute_api<Fq>(input_bases, bases_size, config, output_bases, false);
+}
+
+unsigned long long b200_launch_count(void) { return g_launches; }
+
+} // extern "C"

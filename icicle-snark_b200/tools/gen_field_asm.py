@@ -151,8 +151,9 @@ def block_addp_masked(p):
 
 
 # ----------------------------------------------------------------------------- interpreter
-def run_block(block, env):
-    """Execute a block on a dict name->u32. Mirrors PTX semantics of the used subset."""
+def run_block(block, env, allow_wrap=False):
+    """Execute a block on a dict name->u32. Mirrors PTX semantics of the used subset.
+    A carry out of a non-.cc addc is an error unless allow_wrap (mod-2^256 arithmetic intended)."""
     ops, ins, temps = block
     cc = 0
     reg = dict(env)
@@ -192,7 +193,7 @@ def run_block(block, env):
         if sets_cc:
             cc = cout
         elif uses_cc:
-            if cout and base != "subc":
+            if cout and base != "subc" and not allow_wrap:
                 raise OverflowError(f"carry lost at {i}")
             cc = cc  # PTX leaves CC unchanged without .cc
         reg[d] = res
