@@ -38,3 +38,5 @@ def lib() -> IcicleLib:
     if _lib is None:
         _lib = IcicleLib(LIB_PATH)
     return _lib
+
+from .prover import CacheManager, ZKeyCache, groth16_prove, proof_json, proof_to_dict  # noqa: E402,F401

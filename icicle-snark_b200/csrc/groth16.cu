@@ -1,0 +1,750 @@
+// Fused Groth16 proving path: ZKeyCache (device-resident, Montgomery-form zkey), R1CS evaluation, the
+// quotient chain, the five MSMs, the blinding epilogue and the proof.json/public.json writers.
+//
+// Replaces, behind the b200_groth16_* entry points of include/icicle_b200.h:
+//   /root/reference/src/cache.rs:58-72,117-256,264-289      ZKeyCache / CacheManager
+//   /root/reference/src/proof_helper.rs:31-170              construct_r1cs
+//   /root/reference/src/proof_helper.rs:172-241             groth16_commitments
+//   /root/reference/src/proof_helper.rs:243-317             groth16_prove_helper (epilogue)
+//   /root/reference/src/file_wrapper.rs:45-103,169-237, src/zkey.rs:47-85, src/conversions.rs:30-56, src/lib.rs:33-61
+//
+// What changes relative to the reference's call sequence (same results):
+//   * zkey points stay in the Montgomery form the file already stores them in (the reference converts
+//     them out, cache.rs:208-212); coefficients stay as stored (coef*R^2): a Montgomery product with a
+//     standard-form witness value is then directly the Montgomery form of coef*w.
+//   * A*w, B*w are evaluated on the GPU from a CSR built once per zkey (the reference gathers on the host,
+//     crosses PCIe twice and scatters in a single-thread loop, proof_helper.rs:55-99).
+//   * iNTT -> x keys -> NTT runs on the Stockham passes of ntt.cu with 1/N * keys fused into the last
+//     iNTT pass; A'.B' - C' and the conversion to standard form are one kernel.
+//   * A, B1, C, B2 start as soon as the witness is on the device, concurrently with the quotient chain;
+//     H follows on the chain's stream.  Four streams, no host synchronisation until the five results.
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fcntl.h>
+#include <map>
+#include <mutex>
+#include <random>
+#include <string>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+#include <vector>
+
+#include "host_math.h"
+#include "msm.cuh"
+#include "ntt.cuh"
+#include "staging.cuh"
+
+namespace b200 {
+
+#define B200_LAUNCH(kernel, grid, block, smem, st, ...)                                                                \
+  do {                                                                                                                 \
+    kernel<<<(grid), (block), (smem), (st)>>>(__VA_ARGS__);                                                            \
+    ++g_launches;                                                                                                      \
+  } while (0)
+
+  // ------------------------------------------------------------------------------------------------ binfile
+  struct Section {
+    const uint8_t* p = nullptr;
+    uint64_t size = 0;
+  };
+
+  // iden3 binfile container (file_wrapper.rs:45-103): magic, u32 version, u32 n_sections, then
+  // {u32 id, u64 len, payload}*.  Returns false on malformed input.
+  static bool parse_binfile(const uint8_t* buf, size_t len, const char* magic, uint32_t max_version, std::map<uint32_t, Section>& out)
+  {
+    if (len < 12 || memcmp(buf, magic, 4) != 0) return false;
+    uint32_t version, nsec;
+    memcpy(&version, buf + 4, 4);
+    memcpy(&nsec, buf + 8, 4);
+    if (version > max_version) return false;
+    size_t pos = 12;
+    for (uint32_t i = 0; i < nsec; ++i) {
+      if (pos + 12 > len) return false;
+      uint32_t id;
+      uint64_t sz;
+      memcpy(&id, buf + pos, 4);
+      memcpy(&sz, buf + pos + 4, 8);
+      pos += 12;
+      if (sz > len - pos) return false;
+      if (!out.count(id)) out[id] = {buf + pos, sz}; // first occurrence wins (sections[id][0])
+      pos += sz;
+    }
+    return true;
+  }
+
+  static const uint32_t FR_MODULUS[8] = {0xf0000001, 0x43e1f593, 0x79b97091, 0x2833e848,
+                                         0x8181585d, 0xb85045b6, 0xe131a029, 0x30644e72};
+  static const uint32_t FQ_MODULUS[8] = {0xd87cfd47, 0x3c208c16, 0x6871ca8d, 0x97816a91,
+                                         0x8181585d, 0xb85045b6, 0xe131a029, 0x30644e72};
+
+  // ------------------------------------------------------------------------------------------------ kernels
+  // rows: A row t and B row t evaluated by one thread; out layout as the reference's d_vec:
+  // d[0..N) = B.w, d[N..2N) = A.w, d[2N..3N) = A.w * B.w   (proof_helper.rs:94-114), Montgomery form.
+  // val = coef*R^2 (as stored in the zkey), w standard form: val (x) w = coef*w*R.
+  static __global__ void __launch_bounds__(256) r1cs_eval_kernel(
+    const uint32_t* row_ptr, const uint32_t* col, const Fr* val, const Fr* witness, uint32_t N, Fr* d)
+  {
+    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < N; t += gridDim.x * blockDim.x) {
+      Fr acc[2];
+#pragma unroll
+      for (int m = 0; m < 2; ++m) {
+        uint32_t beg = row_ptr[m * N + t], end = row_ptr[m * N + t + 1];
+        Fr a = Fr::zero();
+        for (uint32_t e = beg; e < end; ++e)
+          a = a + ld_fr(val + e) * ld_fr(witness + col[e]);
+        acc[m] = a;
+      }
+      st_fr(d + N + t, acc[0]);
+      st_fr(d + t, acc[1]);
+      st_fr(d + 2 * (size_t)N + t, acc[0] * acc[1]);
+    }
+  }
+
+  // h[i] = from_mont(a[i]*b[i] - c[i])  (proof_helper.rs:153-167, plus the conversion the MSM digits need)
+  static __global__ void __launch_bounds__(256) quotient_combine_kernel(const Fr* d, uint32_t N, Fr* h)
+  {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) {
+      Fr v = ld_fp_coherent(d + i) * ld_fp_coherent(d + N + i) - ld_fp_coherent(d + 2 * (size_t)N + i);
+      st_fr(h + i, Fr::from_mont(v));
+    }
+  }
+
+  struct PowTab {
+    Fr pw[30];
+  };
+  // keys[i] = scale * g^i  (g^(2^j) table, Montgomery).  Replaces the host loop of cache.rs:264-289.
+  static __global__ void __launch_bounds__(256) powers_kernel(PowTab t, Fr scale, int logn, Fr* out)
+  {
+    size_t n = (size_t)1 << logn;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+      Fr acc = scale;
+      for (int b = 0; b < logn; ++b)
+        if ((i >> b) & 1) acc = acc * t.pw[b];
+      st_fr(out + i, acc);
+    }
+  }
+
+} // namespace b200
+
+using namespace b200;
+
+// ---------------------------------------------------------------------------------------------------- cache
+struct b200_zkey_cache {
+  int device = 0;
+  int rank = 0, world = 1;
+  uint32_t n_vars = 0, n_public = 0, domain_size = 0, power = 0;
+  uint64_t n_coef = 0, device_bytes = 0;
+  int precompute = 1;
+  // verification-key points needed by the epilogue (Montgomery, as stored: zkey.rs:61-69)
+  G1Affine alpha1, beta1, delta1;
+  G2Affine beta2, delta2;
+  // shard [lo,hi) of every base-point section held by this rank
+  uint32_t a_lo = 0, a_hi = 0, c_lo = 0, c_hi = 0, h_lo = 0, h_hi = 0;
+  G1Affine *pA = nullptr, *pB1 = nullptr, *pC = nullptr, *pH = nullptr;
+  G2Affine* pB2 = nullptr;
+  MsmPlan planA, planC, planH, planB2;
+  // R1CS in CSR over rows [A rows 0..N) | B rows 0..N)]
+  uint32_t *row_ptr = nullptr, *col = nullptr;
+  Fr* val = nullptr;
+  Fr* keys = nullptr; // 1/N * w_2N^i, Montgomery
+  // per-proof workspace
+  Fr *d_witness = nullptr, *d_vec = nullptr, *d_h = nullptr;
+  uint8_t* d_results = nullptr; // 4 x G1 projective + 1 x G2 projective
+  uint8_t* h_results = nullptr; // pinned
+  cudaStream_t s_copy = nullptr, s_g1 = nullptr, s_g2 = nullptr, s_q = nullptr;
+  cudaEvent_t ev_wit = nullptr, ev_start = nullptr, ev_h2d = nullptr, ev_r1cs = nullptr, ev_ntt = nullptr, ev_g1 = nullptr,
+              ev_g2 = nullptr, ev_q = nullptr, ev_prev = nullptr;
+  std::mutex mu;
+};
+
+namespace b200 {
+
+  template <class T>
+  static cudaError_t dev_alloc(T** p, size_t count, b200_zkey_cache* c)
+  {
+    size_t bytes = (count ? count : 1) * sizeof(T);
+    cudaError_t e = cudaMalloc((void**)p, bytes);
+    if (e == cudaSuccess) c->device_bytes += bytes;
+    return e;
+  }
+
+  static void shard(uint32_t n, int rank, int world, uint32_t* lo, uint32_t* hi)
+  {
+    *lo = (uint32_t)((uint64_t)n * rank / world);
+    *hi = (uint32_t)((uint64_t)n * (rank + 1) / world);
+  }
+
+  static void cache_free(b200_zkey_cache* c)
+  {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    void* ptrs[] = {c->pA, c->pB1, c->pC, c->pH, c->pB2, c->row_ptr, c->col, c->val, c->keys, c->d_witness, c->d_vec, c->d_h, c->d_results};
+    for (void* p : ptrs)
+      if (p) cudaFree(p);
+    if (c->h_results) cudaFreeHost(c->h_results);
+    cudaStream_t ss[] = {c->s_copy, c->s_g1, c->s_g2, c->s_q};
+    for (auto s : ss)
+      if (s) cudaStreamDestroy(s);
+    cudaEvent_t es[] = {c->ev_wit, c->ev_start, c->ev_h2d, c->ev_r1cs, c->ev_ntt, c->ev_g1, c->ev_g2, c->ev_q, c->ev_prev};
+    for (auto e : es)
+      if (e) cudaEventDestroy(e);
+    delete c;
+  }
+
+  // upload the [lo,hi) slice of a base-point section; with precompute > 1 expand it into the
+  // [i*f + j] = 2^(shift*j) P_i table the MSM consumes (cuda_msm.cuh:29-43 layout)
+  template <class F>
+  static eIcicleError upload_points(
+    b200_zkey_cache* c, const Section& sec, uint32_t lo, uint32_t hi, const MsmPlan& plan, Affine<F>** out, cudaStream_t st)
+  {
+    const size_t n = hi - lo;
+    const int f = plan.factor;
+    B200_CUDA(dev_alloc(out, n * f, c), ICICLE_ALLOCATION_FAILED);
+    if (n == 0) return ICICLE_SUCCESS;
+    const uint8_t* src = sec.p + (size_t)lo * sizeof(Affine<F>);
+    if (f == 1) {
+      B200_CUDA(cudaMemcpyAsync(*out, src, n * sizeof(Affine<F>), cudaMemcpyHostToDevice, st), ICICLE_COPY_FAILED);
+      return ICICLE_SUCCESS;
+    }
+    Affine<F>* tmp = nullptr;
+    B200_CUDA(cudaMallocAsync((void**)&tmp, n * sizeof(Affine<F>), st), ICICLE_ALLOCATION_FAILED);
+    B200_CUDA(cudaMemcpyAsync(tmp, src, n * sizeof(Affine<F>), cudaMemcpyHostToDevice, st), ICICLE_COPY_FAILED);
+    eIcicleError e = precompute_enqueue<F>(tmp, true, (int)n, f, plan.c * plan.sets, *out, true, st);
+    cudaFreeAsync(tmp, st);
+    return e;
+  }
+
+  static eIcicleError cache_build(const uint8_t* zkey, size_t zkey_len, int precompute, int rank, int world, b200_zkey_cache** out)
+  {
+    if (!zkey || !out) return ICICLE_INVALID_POINTER;
+    if (world < 1 || rank < 0 || rank >= world) return ICICLE_INVALID_ARGUMENT;
+    B200_TRY(ensure_device());
+    std::map<uint32_t, Section> sec;
+    if (!parse_binfile(zkey, zkey_len, "zkey", 2, sec)) return ICICLE_INVALID_ARGUMENT;
+    for (uint32_t id : {1u, 2u, 4u, 5u, 6u, 7u, 8u, 9u})
+      if (!sec.count(id)) return ICICLE_INVALID_ARGUMENT;
+    uint32_t protocol = 0;
+    if (sec[1].size < 4) return ICICLE_INVALID_ARGUMENT;
+    memcpy(&protocol, sec[1].p, 4);
+    if (protocol != 1) return ICICLE_INVALID_ARGUMENT; // "Protocol not supported" (file_wrapper.rs:196-208)
+
+    // header (zkey.rs:47-85)
+    const Section& h = sec[2];
+    const size_t need = 4 + 32 + 4 + 32 + 12 + 64 + 64 + 128 + 128 + 64 + 128;
+    if (h.size < need) return ICICLE_INVALID_ARGUMENT;
+    const uint8_t* p = h.p;
+    uint32_t n8q, n8r;
+    memcpy(&n8q, p, 4);
+    if (n8q != 32 || memcmp(p + 4, FQ_MODULUS, 32) != 0) return ICICLE_INVALID_ARGUMENT; // not BN254
+    memcpy(&n8r, p + 36, 4);
+    if (n8r != 32 || memcmp(p + 40, FR_MODULUS, 32) != 0) return ICICLE_INVALID_ARGUMENT;
+    b200_zkey_cache* c = new b200_zkey_cache();
+    c->device = active_device();
+    c->rank = rank;
+    c->world = world;
+    c->precompute = precompute > 1 ? precompute : 1;
+    memcpy(&c->n_vars, p + 72, 4);
+    memcpy(&c->n_public, p + 76, 4);
+    memcpy(&c->domain_size, p + 80, 4);
+    p += 84;
+    memcpy(&c->alpha1, p, 64);
+    memcpy(&c->beta1, p + 64, 64);
+    memcpy(&c->beta2, p + 128, 128);
+    /* gamma2 at p+256 is not used by the prover */
+    memcpy(&c->delta1, p + 384, 64);
+    memcpy(&c->delta2, p + 448, 128);
+    const uint32_t N = c->domain_size;
+    if (N == 0 || (N & (N - 1)) || c->n_vars == 0 || c->n_public + 1 > c->n_vars) {
+      delete c;
+      return ICICLE_INVALID_ARGUMENT;
+    }
+    while ((1u << c->power) < N)
+      ++c->power;
+    if (c->power + 1 > 28) {
+      delete c;
+      return ICICLE_INVALID_ARGUMENT;
+    }
+    const uint32_t n_c = c->n_vars - c->n_public - 1;
+    if (sec[5].size != (uint64_t)c->n_vars * 64 || sec[6].size != (uint64_t)c->n_vars * 64 ||
+        sec[7].size != (uint64_t)c->n_vars * 128 || sec[8].size != (uint64_t)n_c * 64 || sec[9].size != (uint64_t)N * 64 ||
+        sec[4].size < 4) {
+      delete c;
+      return ICICLE_INVALID_ARGUMENT;
+    }
+
+    eIcicleError err = ICICLE_SUCCESS;
+    cudaError_t ce = cudaSuccess;
+    auto fail = [&](eIcicleError e) {
+      cache_free(c);
+      return e;
+    };
+#define CK(call)                                                                                                       \
+  do {                                                                                                                 \
+    ce = (call);                                                                                                       \
+    if (ce != cudaSuccess) {                                                                                           \
+      fprintf(stderr, "[icicle_b200] %s: %s\n", #call, cudaGetErrorString(ce));                                        \
+      return fail(translate(ce, ICICLE_UNKNOWN_FALLBACK));                                                             \
+    }                                                                                                                  \
+  } while (0)
+
+    CK(cudaStreamCreateWithFlags(&c->s_copy, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&c->s_g1, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&c->s_g2, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&c->s_q, cudaStreamNonBlocking));
+    for (cudaEvent_t* e : {&c->ev_wit, &c->ev_prev})
+      CK(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+    for (cudaEvent_t* e : {&c->ev_start, &c->ev_h2d, &c->ev_r1cs, &c->ev_ntt, &c->ev_g1, &c->ev_g2, &c->ev_q})
+      CK(cudaEventCreate(e));
+    cudaStream_t st = c->s_copy;
+
+    // ---- base points: this rank's contiguous shard of every section
+    shard(c->n_vars, rank, world, &c->a_lo, &c->a_hi);
+    shard(n_c, rank, world, &c->c_lo, &c->c_hi);
+    shard(N, rank, world, &c->h_lo, &c->h_hi);
+    auto plan_for = [&](uint32_t n, bool g2) {
+      MsmPlan pl = make_msm_plan(n ? (int)n : 1, 0, 254, 1, g2);
+      if (c->precompute > 1) pl = make_msm_plan(n ? (int)n : 1, pl.c, 254, c->precompute, g2);
+      return pl;
+    };
+    c->planA = plan_for(c->a_hi - c->a_lo, false);
+    c->planC = plan_for(c->c_hi - c->c_lo, false);
+    c->planH = plan_for(c->h_hi - c->h_lo, false);
+    c->planB2 = plan_for(c->a_hi - c->a_lo, true);
+    if ((err = upload_points<Fq>(c, sec[5], c->a_lo, c->a_hi, c->planA, &c->pA, st)) != ICICLE_SUCCESS) return fail(err);
+    if ((err = upload_points<Fq>(c, sec[6], c->a_lo, c->a_hi, c->planA, &c->pB1, st)) != ICICLE_SUCCESS) return fail(err);
+    if ((err = upload_points<Fq2>(c, sec[7], c->a_lo, c->a_hi, c->planB2, &c->pB2, st)) != ICICLE_SUCCESS) return fail(err);
+    if ((err = upload_points<Fq>(c, sec[8], c->c_lo, c->c_hi, c->planC, &c->pC, st)) != ICICLE_SUCCESS) return fail(err);
+    if ((err = upload_points<Fq>(c, sec[9], c->h_lo, c->h_hi, c->planH, &c->pH, st)) != ICICLE_SUCCESS) return fail(err);
+
+    // ---- coefficients -> CSR (record layout: cache.rs:126-166)
+    const Section& cs = sec[4];
+    const size_t s_coef = 12 + 32;
+    uint32_t declared = 0;
+    memcpy(&declared, cs.p, 4);
+    c->n_coef = (cs.size - 4) / s_coef;
+    const uint8_t* rec = cs.p + 4;
+    std::vector<uint32_t> row_ptr(2 * (size_t)N + 1, 0);
+    for (uint64_t i = 0; i < c->n_coef; ++i) {
+      const uint8_t* r = rec + i * s_coef;
+      uint32_t m = r[0], row, sig;
+      memcpy(&row, r + 4, 4);
+      memcpy(&sig, r + 8, 4);
+      if (m > 1 || row >= N || sig >= c->n_vars) return fail(ICICLE_INVALID_ARGUMENT);
+      ++row_ptr[(size_t)m * N + row + 1];
+    }
+    for (size_t i = 0; i < 2 * (size_t)N; ++i)
+      row_ptr[i + 1] += row_ptr[i];
+    std::vector<uint32_t> cur(row_ptr.begin(), row_ptr.end() - 1);
+    std::vector<uint32_t> col(c->n_coef ? c->n_coef : 1);
+    std::vector<Fr> val(c->n_coef ? c->n_coef : 1);
+    for (uint64_t i = 0; i < c->n_coef; ++i) {
+      const uint8_t* r = rec + i * s_coef;
+      uint32_t m = r[0], row, sig;
+      memcpy(&row, r + 4, 4);
+      memcpy(&sig, r + 8, 4);
+      uint32_t pos = cur[(size_t)m * N + row]++;
+      col[pos] = sig;
+      memcpy(&val[pos], r + 12, 32);
+    }
+    CK(dev_alloc(&c->row_ptr, row_ptr.size(), c));
+    CK(dev_alloc(&c->col, col.size(), c));
+    CK(dev_alloc(&c->val, val.size(), c));
+    CK(cudaMemcpyAsync(c->row_ptr, row_ptr.data(), row_ptr.size() * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(c->col, col.data(), col.size() * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(c->val, val.data(), val.size() * sizeof(Fr), cudaMemcpyHostToDevice, st));
+
+    // ---- coset powers with 1/N folded in: keys[i] = N^-1 * w_2N^i, w_2N = W[power+1] (cache.rs:168-169,220-226)
+    {
+      PowTab t;
+      Fr g = Fr::to_mont(host_omega((int)c->power + 1));
+      for (int i = 0; i < 30; ++i) {
+        t.pw[i] = g;
+        g = g.sqr();
+      }
+      Fr two = Fr::one().dbl(), nn = Fr::one();
+      for (uint32_t i = 0; i < c->power; ++i)
+        nn = nn * two;
+      CK(dev_alloc(&c->keys, (size_t)N, c));
+      B200_LAUNCH(powers_kernel, grid_for(N, 256, 8), 256, 0, st, t, nn.inverse(), (int)c->power, c->keys);
+    }
+
+    // ---- NTT domain of order N (cache.rs:242-256 sizes it from points_a.len(); domain_size is what the
+    //      transforms need - SURVEY App. C). A larger existing domain is kept; a smaller one is replaced.
+    {
+      const NttDomain* d = ntt_domain();
+      if (d && d->max_log < (int)c->power) bn254_ntt_release_domain();
+      if ((err = ntt_init_domain_host(host_omega((int)c->power), st)) != ICICLE_SUCCESS) return fail(err);
+    }
+
+    // ---- workspace
+    CK(dev_alloc(&c->d_witness, (size_t)c->n_vars, c));
+    CK(dev_alloc(&c->d_vec, 3 * (size_t)N, c));
+    CK(dev_alloc(&c->d_h, (size_t)N, c));
+    CK(dev_alloc(&c->d_results, (size_t)4 * 96 + 192, c));
+    CK(cudaHostAlloc((void**)&c->h_results, 4 * 96 + 192, cudaHostAllocDefault));
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(st)); // host vectors go out of scope
+    CK(cudaEventRecord(c->ev_prev, st));
+#undef CK
+    *out = c;
+    return ICICLE_SUCCESS;
+  }
+
+  // ---------------------------------------------------------------------------------------------- prove
+  static eIcicleError commit_partials(
+    b200_zkey_cache* c, const bn254_scalar_t* witness, uint32_t n_witness, b200_groth16_partials* out, b200_prove_timings* tm)
+  {
+    if (!c || !witness || !out) return ICICLE_INVALID_POINTER;
+    if (n_witness != c->n_vars) return ICICLE_INVALID_ARGUMENT; // "Invalid witness length" (proof_helper.rs:259-264)
+    std::lock_guard<std::mutex> g(c->mu);
+    B200_CUDA(cudaSetDevice(c->device), ICICLE_INVALID_DEVICE);
+    const uint32_t N = c->domain_size;
+    G1Projective* r_a = (G1Projective*)c->d_results;
+    G1Projective *r_b1 = r_a + 1, *r_c = r_a + 2, *r_h = r_a + 3;
+    G2Projective* r_b2 = (G2Projective*)(c->d_results + 4 * 96);
+
+    // witness H2D (proof_helper.rs:194-196); everything else waits on it
+    B200_CUDA(cudaEventRecord(c->ev_start, c->s_copy), ICICLE_UNKNOWN_FALLBACK);
+    B200_CUDA(
+      cudaMemcpyAsync(c->d_witness, witness, (size_t)c->n_vars * 32, cudaMemcpyHostToDevice, c->s_copy), ICICLE_COPY_FAILED);
+    B200_CUDA(cudaEventRecord(c->ev_h2d, c->s_copy), ICICLE_UNKNOWN_FALLBACK);
+    for (cudaStream_t s : {c->s_g1, c->s_g2, c->s_q})
+      B200_CUDA(cudaStreamWaitEvent(s, c->ev_h2d, 0), ICICLE_UNKNOWN_FALLBACK);
+
+    // quotient chain + H on s_q
+    eIcicleError err = ICICLE_SUCCESS;
+    B200_LAUNCH(r1cs_eval_kernel, grid_for(N, 256, 8), 256, 0, c->s_q, c->row_ptr, c->col, c->val, c->d_witness, N, c->d_vec);
+    cudaEventRecord(c->ev_r1cs, c->s_q);
+    if ((err = ntt_enqueue(c->d_vec, c->d_vec, (int)c->power, true, 3, false, c->keys, c->s_q)) != ICICLE_SUCCESS) return err;
+    if ((err = ntt_enqueue(c->d_vec, c->d_vec, (int)c->power, false, 3, false, nullptr, c->s_q)) != ICICLE_SUCCESS) return err;
+    B200_LAUNCH(quotient_combine_kernel, grid_for(N, 256, 8), 256, 0, c->s_q, c->d_vec, N, c->d_h);
+    cudaEventRecord(c->ev_ntt, c->s_q);
+    if (c->h_hi > c->h_lo) {
+      if ((err = msm_enqueue<Fq>(c->planH, c->d_h + c->h_lo, false, c->pH, r_h, c->s_q)) != ICICLE_SUCCESS) return err;
+    }
+    cudaEventRecord(c->ev_q, c->s_q);
+
+    // witness-only MSMs: A, B1, C on s_g1; B2 on s_g2 (proof_helper.rs:198-206)
+    const Fr* w = c->d_witness;
+    if (c->a_hi > c->a_lo) {
+      if ((err = msm_enqueue<Fq>(c->planA, w + c->a_lo, false, c->pA, r_a, c->s_g1)) != ICICLE_SUCCESS) return err;
+      if ((err = msm_enqueue<Fq>(c->planA, w + c->a_lo, false, c->pB1, r_b1, c->s_g1)) != ICICLE_SUCCESS) return err;
+      if ((err = msm_enqueue<Fq2>(c->planB2, w + c->a_lo, false, c->pB2, r_b2, c->s_g2)) != ICICLE_SUCCESS) return err;
+    }
+    if (c->c_hi > c->c_lo) {
+      if ((err = msm_enqueue<Fq>(c->planC, w + c->n_public + 1 + c->c_lo, false, c->pC, r_c, c->s_g1)) != ICICLE_SUCCESS)
+        return err;
+    }
+    cudaEventRecord(c->ev_g1, c->s_g1);
+    cudaEventRecord(c->ev_g2, c->s_g2);
+
+    // join on s_copy, one D2H of the five partial sums
+    for (cudaEvent_t e : {c->ev_q, c->ev_g1, c->ev_g2})
+      B200_CUDA(cudaStreamWaitEvent(c->s_copy, e, 0), ICICLE_UNKNOWN_FALLBACK);
+    B200_CUDA(
+      cudaMemcpyAsync(c->h_results, c->d_results, 4 * 96 + 192, cudaMemcpyDeviceToHost, c->s_copy), ICICLE_COPY_FAILED);
+    B200_CUDA(cudaEventRecord(c->ev_prev, c->s_copy), ICICLE_UNKNOWN_FALLBACK);
+    B200_CUDA(cudaStreamSynchronize(c->s_copy), ICICLE_SYNCHRONIZATION_FAILED);
+    B200_CUDA(cudaGetLastError(), ICICLE_UNKNOWN_FALLBACK);
+
+    // empty shards contribute the identity
+    G1Projective id1 = {Fq::zero(), Fq::raw_one(), Fq::zero()};
+    G2Projective id2 = {Fq2::zero(), {Fq::raw_one(), Fq::zero()}, Fq2::zero()};
+    memcpy(out, c->h_results, 4 * 96 + 192);
+    if (c->a_hi == c->a_lo) {
+      memcpy(&out->a, &id1, 96);
+      memcpy(&out->b1, &id1, 96);
+      memcpy(&out->b2, &id2, 192);
+    }
+    if (c->c_hi == c->c_lo) memcpy(&out->c, &id1, 96);
+    if (c->h_hi == c->h_lo) memcpy(&out->h, &id1, 96);
+    if (tm) {
+      cudaEventSynchronize(c->ev_q);
+      cudaEventSynchronize(c->ev_g1);
+      cudaEventSynchronize(c->ev_g2);
+      float t_q = 0, t_g1 = 0, t_g2 = 0;
+      cudaEventElapsedTime(&tm->h2d_ms, c->ev_start, c->ev_h2d);
+      cudaEventElapsedTime(&tm->r1cs_ms, c->ev_h2d, c->ev_r1cs);
+      cudaEventElapsedTime(&tm->ntt_ms, c->ev_r1cs, c->ev_ntt);
+      cudaEventElapsedTime(&t_q, c->ev_start, c->ev_q);
+      cudaEventElapsedTime(&t_g1, c->ev_start, c->ev_g1);
+      cudaEventElapsedTime(&t_g2, c->ev_start, c->ev_g2);
+      tm->msm_g1_ms = t_g1;
+      tm->msm_g2_ms = t_g2;
+      tm->total_ms = std::max(t_q, std::max(t_g1, t_g2));
+    }
+    return ICICLE_SUCCESS;
+  }
+
+  template <class F>
+  static XYZZ<F> load_partial(const void* p)
+  {
+    Projective<F> pr;
+    memcpy(&pr, p, sizeof(pr));
+    return xyzz_from_projective(proj_to_mont(pr));
+  }
+
+  // Blinding epilogue (proof_helper.rs:274-295) on the host; ~6 scalar multiplications.
+  static eIcicleError finish(
+    const b200_zkey_cache* c, const b200_groth16_partials* parts, int n_parts, const bn254_scalar_t* r_in,
+    const bn254_scalar_t* s_in, b200_groth16_proof* proof)
+  {
+    if (!c || !parts || !proof) return ICICLE_INVALID_POINTER;
+    if (n_parts < 1) return ICICLE_INVALID_ARGUMENT;
+    Fr r, s;
+    if (r_in && s_in) {
+      memcpy(&r, r_in, 32);
+      memcpy(&s, s_in, 32);
+    } else { // ScalarCfg::generate_random(2) (proof_helper.rs:276-278)
+      std::mt19937_64 rng(std::random_device{}());
+      r = host_random_fr(rng);
+      s = host_random_fr(rng);
+    }
+    G1XYZZ A = G1XYZZ::inf(), B1 = G1XYZZ::inf(), C = G1XYZZ::inf(), H = G1XYZZ::inf();
+    G2XYZZ B2 = G2XYZZ::inf();
+    for (int i = 0; i < n_parts; ++i) { // fold the per-rank partial sums
+      A.add(load_partial<Fq>(&parts[i].a));
+      B1.add(load_partial<Fq>(&parts[i].b1));
+      C.add(load_partial<Fq>(&parts[i].c));
+      H.add(load_partial<Fq>(&parts[i].h));
+      B2.add(load_partial<Fq2>(&parts[i].b2));
+    }
+    G1XYZZ d1 = G1XYZZ::from_affine(c->delta1);
+    G2XYZZ d2 = G2XYZZ::from_affine(c->delta2);
+    // pi_a = A + alpha1 + r*delta1
+    G1XYZZ pi_a = A;
+    pi_a.madd(c->alpha1);
+    pi_a.add(host_scalar_mul(d1, r));
+    // pi_b = B2 + beta2 + s*delta2
+    G2XYZZ pi_b = B2;
+    pi_b.madd(c->beta2);
+    pi_b.add(host_scalar_mul(d2, s));
+    // pi_b1 = B1 + beta1 + s*delta1
+    G1XYZZ pi_b1 = B1;
+    pi_b1.madd(c->beta1);
+    pi_b1.add(host_scalar_mul(d1, s));
+    // pi_c = C + H + s*pi_a + r*pi_b1 - (r*s)*delta1
+    Fr rs = Fr::from_mont(Fr::to_mont(r) * Fr::to_mont(s));
+    G1XYZZ pi_c = C;
+    pi_c.add(H);
+    pi_c.add(host_scalar_mul(pi_a, s));
+    pi_c.add(host_scalar_mul(pi_b1, r));
+    pi_c.add(host_scalar_mul(d1, rs).neg());
+
+    G1Affine a = affine_from_mont(pi_a.to_affine());
+    G2Affine b = affine_from_mont(pi_b.to_affine());
+    G1Affine cc = affine_from_mont(pi_c.to_affine());
+    memcpy(&proof->pi_a, &a, 64);
+    memcpy(&proof->pi_b, &b, 128);
+    memcpy(&proof->pi_c, &cc, 64);
+    return ICICLE_SUCCESS;
+  }
+
+  // ---------------------------------------------------------------------------------------------- files + JSON
+  struct MappedFile {
+    const uint8_t* p = nullptr;
+    size_t len = 0;
+    int fd = -1;
+    bool open(const char* path)
+    {
+      fd = ::open(path, O_RDONLY);
+      if (fd < 0) return false;
+      struct stat sb;
+      if (fstat(fd, &sb) != 0 || sb.st_size <= 0) return false;
+      len = (size_t)sb.st_size;
+      void* m = mmap(nullptr, len, PROT_READ, MAP_PRIVATE, fd, 0);
+      if (m == MAP_FAILED) return false;
+      p = (const uint8_t*)m;
+      return true;
+    }
+    ~MappedFile()
+    {
+      if (p) munmap((void*)p, len);
+      if (fd >= 0) ::close(fd);
+    }
+  };
+
+  // 256-bit little-endian limbs -> base-10 string (BigUint::to_str_radix(10), conversions.rs:30-39)
+  static std::string to_decimal(const uint32_t limbs[8])
+  {
+    uint32_t v[8];
+    memcpy(v, limbs, 32);
+    std::string out;
+    bool zero = true;
+    for (int i = 0; i < 8; ++i)
+      zero = zero && v[i] == 0;
+    if (zero) return "0";
+    char chunk[16];
+    std::vector<uint32_t> parts;
+    for (;;) {
+      bool z = true;
+      uint64_t rem = 0;
+      for (int i = 7; i >= 0; --i) {
+        uint64_t cur = (rem << 32) | v[i];
+        v[i] = (uint32_t)(cur / 1000000000u);
+        rem = cur % 1000000000u;
+        z = z && v[i] == 0;
+      }
+      parts.push_back((uint32_t)rem);
+      if (z) break;
+    }
+    snprintf(chunk, sizeof chunk, "%u", parts.back());
+    out = chunk;
+    for (size_t i = parts.size() - 1; i-- > 0;) {
+      snprintf(chunk, sizeof chunk, "%09u", parts[i]);
+      out += chunk;
+    }
+    return out;
+  }
+
+  // serde_json::to_writer_pretty of json!(Proof): alphabetical keys, 2-space indent, no trailing newline
+  // (proof_helper.rs:308-316, file_wrapper.rs:105-113)
+  static std::string proof_json(const b200_groth16_proof& pr)
+  {
+    auto fq = [&](const bn254_fq_t& x) { return "\"" + to_decimal(x.limbs) + "\""; };
+    std::string s = "{\n  \"curve\": \"bn128\",\n";
+    s += "  \"pi_a\": [\n    " + fq(pr.pi_a.x) + ",\n    " + fq(pr.pi_a.y) + ",\n    \"1\"\n  ],\n";
+    s += "  \"pi_b\": [\n    [\n      " + fq(pr.pi_b.x.c0) + ",\n      " + fq(pr.pi_b.x.c1) + "\n    ],\n    [\n      " +
+         fq(pr.pi_b.y.c0) + ",\n      " + fq(pr.pi_b.y.c1) + "\n    ],\n    [\n      \"1\",\n      \"0\"\n    ]\n  ],\n";
+    s += "  \"pi_c\": [\n    " + fq(pr.pi_c.x) + ",\n    " + fq(pr.pi_c.y) + ",\n    \"1\"\n  ],\n";
+    s += "  \"protocol\": \"groth16\"\n}";
+    return s;
+  }
+
+  static std::string public_json(const uint8_t* witness_section, uint32_t n_public)
+  {
+    if (n_public == 0) return "[]";
+    std::string s = "[\n";
+    for (uint32_t i = 1; i <= n_public; ++i) {
+      uint32_t limbs[8];
+      memcpy(limbs, witness_section + (size_t)i * 32, 32);
+      s += "  \"" + to_decimal(limbs) + "\"";
+      s += i < n_public ? ",\n" : "\n";
+    }
+    s += "]";
+    return s;
+  }
+
+  static bool write_file(const char* path, const std::string& s)
+  {
+    FILE* f = fopen(path, "wb");
+    if (!f) return false;
+    bool ok = fwrite(s.data(), 1, s.size(), f) == s.size();
+    return fclose(f) == 0 && ok;
+  }
+
+  // process-wide CacheManager keyed "{zkey}_{device}" (src/lib.rs:44-52, cache.rs:110-114)
+  static std::mutex g_cm_mu;
+  static std::map<std::string, b200_zkey_cache*> g_cache_manager;
+
+} // namespace b200
+
+extern "C" {
+
+eIcicleError b200_zkey_cache_create(const uint8_t* zkey, size_t zkey_len, int precompute, b200_zkey_cache** out)
+{
+  return cache_build(zkey, zkey_len, precompute, 0, 1, out);
+}
+
+eIcicleError
+b200_zkey_cache_create_sharded(const uint8_t* zkey, size_t zkey_len, int precompute, int rank, int world, b200_zkey_cache** out)
+{
+  return cache_build(zkey, zkey_len, precompute, rank, world, out);
+}
+
+eIcicleError b200_zkey_cache_destroy(b200_zkey_cache* cache)
+{
+  cache_free(cache);
+  return ICICLE_SUCCESS;
+}
+
+eIcicleError b200_zkey_cache_info(
+  const b200_zkey_cache* c, uint32_t* n_vars, uint32_t* n_public, uint32_t* domain_size, uint64_t* n_coef, uint64_t* device_bytes)
+{
+  if (!c) return ICICLE_INVALID_POINTER;
+  if (n_vars) *n_vars = c->n_vars;
+  if (n_public) *n_public = c->n_public;
+  if (domain_size) *domain_size = c->domain_size;
+  if (n_coef) *n_coef = c->n_coef;
+  if (device_bytes) *device_bytes = c->device_bytes;
+  return ICICLE_SUCCESS;
+}
+
+eIcicleError b200_groth16_commit_partials(
+  b200_zkey_cache* cache, const bn254_scalar_t* witness, uint32_t n_witness, b200_groth16_partials* out, b200_prove_timings* tm)
+{
+  return commit_partials(cache, witness, n_witness, out, tm);
+}
+
+eIcicleError b200_groth16_finish(
+  const b200_zkey_cache* cache, const b200_groth16_partials* parts, int n_parts, const bn254_scalar_t* r,
+  const bn254_scalar_t* s, b200_groth16_proof* proof)
+{
+  return finish(cache, parts, n_parts, r, s, proof);
+}
+
+eIcicleError b200_groth16_prove(
+  b200_zkey_cache* cache, const bn254_scalar_t* witness, uint32_t n_witness, const bn254_scalar_t* r, const bn254_scalar_t* s,
+  b200_groth16_proof* proof, b200_prove_timings* tm)
+{
+  if (!cache || !proof) return ICICLE_INVALID_POINTER;
+  if (cache->world != 1) return ICICLE_INVALID_ARGUMENT; // sharded caches go through commit_partials + finish
+  b200_groth16_partials parts;
+  B200_TRY(commit_partials(cache, witness, n_witness, &parts, tm));
+  return finish(cache, &parts, 1, r, s, proof);
+}
+
+eIcicleError b200_groth16_prove_files(
+  const char* witness_path, const char* zkey_path, const char* proof_path, const char* public_path, const char* device)
+{
+  if (!witness_path || !zkey_path || !proof_path || !public_path || !device) return ICICLE_INVALID_POINTER;
+  if (strncmp(device, "CUDA", 4) != 0) return ICICLE_INVALID_DEVICE; // no CPU backend behind this library
+  icicleDevice dev;
+  memset(&dev, 0, sizeof dev);
+  strncpy(dev.type, "CUDA", sizeof dev.type - 1);
+  dev.id = 0; // src/lib.rs:29
+  B200_TRY(icicle_set_device(&dev));
+
+  b200_zkey_cache* cache = nullptr;
+  {
+    std::lock_guard<std::mutex> g(g_cm_mu);
+    std::string key = std::string(zkey_path) + "_" + device;
+    auto it = g_cache_manager.find(key);
+    if (it == g_cache_manager.end()) {
+      MappedFile zk;
+      if (!zk.open(zkey_path)) return ICICLE_INVALID_ARGUMENT;
+      const char* pf = getenv("B200_PRECOMPUTE");
+      B200_TRY(cache_build(zk.p, zk.len, pf ? atoi(pf) : 1, 0, 1, &cache));
+      g_cache_manager[key] = cache;
+    } else {
+      cache = it->second;
+    }
+  }
+  MappedFile wt;
+  if (!wt.open(witness_path)) return ICICLE_INVALID_ARGUMENT;
+  std::map<uint32_t, Section> sec;
+  if (!parse_binfile(wt.p, wt.len, "wtns", 2, sec) || !sec.count(1) || !sec.count(2)) return ICICLE_INVALID_ARGUMENT;
+  // header: u32 n8, n8 bytes prime, u32 n_witness (file_wrapper.rs:169-177)
+  if (sec[1].size < 40) return ICICLE_INVALID_ARGUMENT;
+  uint32_t n8, n_witness;
+  memcpy(&n8, sec[1].p, 4);
+  if (n8 != 32 || memcmp(sec[1].p + 4, FR_MODULUS, 32) != 0) return ICICLE_INVALID_ARGUMENT; // curve mismatch
+  memcpy(&n_witness, sec[1].p + 36, 4);
+  if (sec[2].size < (uint64_t)n_witness * 32) return ICICLE_INVALID_ARGUMENT;
+  b200_groth16_proof proof;
+  const char* fixed = getenv("B200_NO_RANDOMNESS"); // the reference's `no-randomness` cargo feature: r = s = 1
+  bn254_scalar_t one;
+  memset(&one, 0, sizeof one);
+  one.limbs[0] = 1;
+  B200_TRY(b200_groth16_prove(
+    cache, (const bn254_scalar_t*)sec[2].p, n_witness, fixed ? &one : nullptr, fixed ? &one : nullptr, &proof, nullptr));
+  if (!write_file(proof_path, proof_json(proof))) return ICICLE_INVALID_ARGUMENT;
+  if (!write_file(public_path, public_json(sec[2].p, cache->n_public))) return ICICLE_INVALID_ARGUMENT;
+  return ICICLE_SUCCESS;
+}
+
+} // extern "C"

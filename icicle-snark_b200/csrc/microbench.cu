@@ -1,0 +1,152 @@
+// Arithmetic-pipe microbenchmarks: the roofline denominators for MSM/NTT ("measure with an
+// IMAD microbenchmark like MEASURED_PEAKS does for HBM"). Independent register chains, no memory traffic.
+//   mode 0: mad.lo.u32   (IMAD)            mode 1: mad.wide.u32 (IMAD.WIDE, 32x32+64)
+//   mode 2: mad.hi.u32   (IMAD.HI)         mode 3: fma.rn.f64   (DFMA)
+//   mode 4: 4 IMAD.WIDE chains + 4 DFMA chains interleaved (do the two pipes issue concurrently?)
+//   mode 5: mad.lo.cc/madc.hi pairs as the field multiplier emits them (IMAD.WIDE.U32.X carry chains)
+#include "common.cuh"
+
+namespace b200 {
+
+  template <int MODE>
+  __global__ void __launch_bounds__(256) pipe_kernel(uint64_t* out, int iters, uint32_t seed)
+  {
+    uint32_t b = (threadIdx.x * 2654435761u + seed) | 1u, c = blockIdx.x + 12345u;
+    uint64_t sink = 0;
+    if (MODE == 0 || MODE == 2) {
+      uint32_t a[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        a[k] = threadIdx.x + k;
+      for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          if (MODE == 0)
+            asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(a[k]) : "r"(b), "r"(c));
+          else
+            asm volatile("mad.hi.u32 %0, %0, %1, %2;" : "+r"(a[k]) : "r"(b), "r"(c));
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        sink ^= a[k];
+    } else if (MODE == 1) {
+      uint64_t a[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        a[k] = threadIdx.x + k;
+      for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(a[k]) : "r"(b), "r"(c));
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        sink ^= a[k];
+    } else if (MODE == 3) {
+      double a[8], fb = 1.0 + 1e-9 * b, fc = 1e-3 * c;
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        a[k] = threadIdx.x + k;
+      for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          asm volatile("fma.rn.f64 %0, %0, %1, %2;" : "+d"(a[k]) : "d"(fb), "d"(fc));
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        sink ^= (uint64_t)__double_as_longlong(a[k]);
+    } else if (MODE == 4) {
+      uint64_t a[4];
+      double d[4], fb = 1.0 + 1e-9 * b, fc = 1e-3 * c;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        a[k] = threadIdx.x + k;
+        d[k] = threadIdx.x + k;
+      }
+      for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(a[k]) : "r"(b), "r"(c));
+          asm volatile("fma.rn.f64 %0, %0, %1, %2;" : "+d"(d[k]) : "d"(fb), "d"(fc));
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        sink ^= a[k] ^ (uint64_t)__double_as_longlong(d[k]);
+    } else {
+      uint32_t lo[8], hi[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        lo[k] = threadIdx.x + k;
+        hi[k] = k;
+      }
+      for (int i = 0; i < iters; ++i) {
+        // one 8-product carry chain per iteration, like a multiplier row: counts as 8 wide multiply-adds
+        asm volatile(
+          "mad.lo.cc.u32 %0, %16, %17, %0;\n\tmadc.hi.cc.u32 %1, %16, %17, %1;\n\t"
+          "madc.lo.cc.u32 %2, %16, %18, %2;\n\tmadc.hi.cc.u32 %3, %16, %18, %3;\n\t"
+          "madc.lo.cc.u32 %4, %16, %17, %4;\n\tmadc.hi.cc.u32 %5, %16, %17, %5;\n\t"
+          "madc.lo.cc.u32 %6, %16, %18, %6;\n\tmadc.hi.cc.u32 %7, %16, %18, %7;\n\t"
+          "madc.lo.cc.u32 %8, %16, %17, %8;\n\tmadc.hi.cc.u32 %9, %16, %17, %9;\n\t"
+          "madc.lo.cc.u32 %10, %16, %18, %10;\n\tmadc.hi.cc.u32 %11, %16, %18, %11;\n\t"
+          "madc.lo.cc.u32 %12, %16, %17, %12;\n\tmadc.hi.cc.u32 %13, %16, %17, %13;\n\t"
+          "madc.lo.cc.u32 %14, %16, %18, %14;\n\tmadc.hi.u32 %15, %16, %18, %15;\n\t"
+          : "+r"(lo[0]), "+r"(hi[0]), "+r"(lo[1]), "+r"(hi[1]), "+r"(lo[2]), "+r"(hi[2]), "+r"(lo[3]), "+r"(hi[3]),
+            "+r"(lo[4]), "+r"(hi[4]), "+r"(lo[5]), "+r"(hi[5]), "+r"(lo[6]), "+r"(hi[6]), "+r"(lo[7]), "+r"(hi[7])
+          : "r"(b), "r"(c), "r"(seed));
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        sink ^= lo[k] ^ ((uint64_t)hi[k] << 32);
+    }
+    if (sink == 0x123456789abcdefull) out[0] = sink;
+  }
+
+  template <int MODE>
+  static void launch_pipe(uint64_t* d, int iters, int blocks, int rep)
+  {
+    pipe_kernel<MODE><<<blocks, 256>>>(d, iters, rep);
+  }
+
+} // namespace b200
+
+using namespace b200;
+
+// measured operations per second for the given mode on the active device (mode 4 counts both kinds); <0 on error
+extern "C" double b200_pipe_peak(int mode)
+{
+  if (ensure_device() != ICICLE_SUCCESS) return -1.0;
+  uint64_t* d = nullptr;
+  if (cudaMalloc((void**)&d, 64) != cudaSuccess) return -1.0;
+  const int iters = 4096, blocks = sm_count() * 8;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  double best = -1.0;
+  for (int rep = 0; rep < 5; ++rep) {
+    cudaEventRecord(e0, 0);
+    switch (mode) {
+    case 0: launch_pipe<0>(d, iters, blocks, rep); break;
+    case 1: launch_pipe<1>(d, iters, blocks, rep); break;
+    case 2: launch_pipe<2>(d, iters, blocks, rep); break;
+    case 3: launch_pipe<3>(d, iters, blocks, rep); break;
+    case 4: launch_pipe<4>(d, iters, blocks, rep); break;
+    default: launch_pipe<5>(d, iters, blocks, rep); break;
+    }
+    cudaEventRecord(e1, 0);
+    if (cudaEventSynchronize(e1) != cudaSuccess) break;
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    double ops = (double)blocks * 256 * iters * 8;
+    double rate = ops / (ms * 1e-3);
+    if (rate > best) best = rate;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(d);
+  return best;
+}
+
+// the roofline denominator used by bench.py: wide (32x32+64) multiply-adds per second in carry chains
+extern "C" double b200_imad_peak(int wide) { return b200_pipe_peak(wide ? 5 : 0); }

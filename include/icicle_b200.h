@@ -285,6 +285,18 @@ eIcicleError b200_groth16_finish(const b200_zkey_cache* cache, const b200_groth1
 eIcicleError b200_groth16_prove_files(const char* witness_path, const char* zkey_path, const char* proof_path,
                                       const char* public_path, const char* device);
 
+/* Synthetic-setup / test tool: out[i] = k_i * G1 (64 B affine) or k_i * G2 (128 B affine),
+ * k in standard form, host or icicle_malloc'd memory; output Montgomery (as .zkey stores) or standard form.
+ * The reference generates its benchmark zkeys with snarkjs (scripts/setup.sh), which is unavailable offline. */
+eIcicleError b200_fixed_base_mul(const bn254_scalar_t* k, uint64_t n, int g2, int out_montgomery, void* out);
+
+/* Measured arithmetic-pipe peaks (operations/s) for the roofline: mode 0 IMAD, 1 IMAD.WIDE, 2 IMAD.HI, 3 DFMA,
+ * 4 IMAD.WIDE+DFMA co-issue, 5 carry-chained wide multiply-adds. b200_imad_peak(wide) = mode 5 / mode 0. */
+double b200_pipe_peak(int mode);
+double b200_imad_peak(int wide);
+/* kernel launches issued by this library since load (bench.py's gpu_launches) */
+unsigned long long b200_launch_count(void);
+
 /* library identification: returns a static string "icicle-snark-b200 <version> sm_100a" */
 const char* b200_version(void);
 

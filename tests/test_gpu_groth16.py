@@ -1,0 +1,125 @@
+"""GPU: the fused proving path (b200_groth16_*) through the C ABI against the committed golden proofs
+(byte-identical proof.json for fixed blinding factors), against the oracle pipeline on freshly generated
+instances, and under the reference's pairing check for random blinding."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+import icicle_snark_b200 as pkg
+from oracle import groth16_ref as G
+from test_groth16_oracle import FIXED_R, FIXED_S, GOLD, load
+from tools import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def wtns_words(wtns):
+    return G.parse_wtns(wtns)["w"]
+
+
+@pytest.mark.parametrize("n", [6, 100])
+@pytest.mark.parametrize("precompute", [1, 4])
+def test_golden_proofs_byte_identical(gpu, ref, n, precompute):
+    zkey, wtns, vk, gold11, goldrs, goldpub = load(n)
+    cache = pkg.ZKeyCache(gpu, zkey, precompute=precompute)
+    try:
+        assert (cache.n_vars, cache.n_public) == (n + 2, 1)
+        w = wtns_words(wtns)
+        p11, tm = cache.prove(w, 1, 1)
+        assert pkg.proof_json(p11) == gold11
+        prs, _ = cache.prove(w, FIXED_R, FIXED_S)
+        assert pkg.proof_json(prs) == goldrs
+        # random blinding (r = s = NULL): different proofs, both verify under the reference's pairing
+        pa, _ = cache.prove(w)
+        pb, _ = cache.prove(w)
+        assert pkg.proof_json(pa) != pkg.proof_json(pb)
+        public = [int(x) for x in eval(goldpub)]
+        for p in (pa, pb, p11):
+            assert G.verify(ref, pkg.proof_to_dict(p), public, vk)
+        with pytest.raises(pkg.IcicleError):
+            cache.prove(np.ascontiguousarray(w[:-1]), 1, 1)  # "Invalid witness length"
+    finally:
+        cache.close()
+
+
+def test_file_level_api_matches_golden(gpu, tmp_path, monkeypatch):
+    # groth16_prove(witness, zkey, proof, public, device, &mut CacheManager) (src/lib.rs:33-61), C writer
+    base = os.path.join(GOLD, "complex_100")
+    monkeypatch.setenv("B200_NO_RANDOMNESS", "1")
+    proof_p, public_p = str(tmp_path / "proof.json"), str(tmp_path / "public.json")
+    for _ in range(2):  # second call hits the process-wide cache
+        rc = gpu.dll.b200_groth16_prove_files((base + ".wtns").encode(), (base + ".zkey").encode(), proof_p.encode(),
+                                              public_p.encode(), b"CUDA")
+        assert rc == 0
+        assert open(proof_p).read() == open(base + ".proof_r1s1.json").read()
+        assert open(public_p).read() == open(base + ".public.json").read()
+    assert gpu.dll.b200_groth16_prove_files(b"/nonexistent.wtns", (base + ".zkey").encode(), proof_p.encode(),
+                                            public_p.encode(), b"CUDA") != 0
+    assert gpu.dll.b200_groth16_prove_files((base + ".wtns").encode(), (base + ".zkey").encode(), proof_p.encode(),
+                                            public_p.encode(), b"CPU") == 1  # no CPU backend
+    # python mirror of the same entry point
+    cm = pkg.CacheManager(gpu)
+    pkg.groth16_prove(base + ".wtns", base + ".zkey", proof_p, public_p, "CUDA", cm, r=FIXED_R, s=FIXED_S)
+    assert open(proof_p).read() == open(base + ".proof_rs.json").read()
+    with pytest.raises(pkg.IcicleError):
+        pkg.groth16_prove(base + ".wtns", base + ".zkey", proof_p, public_p, "CPU", cm)
+
+
+@pytest.mark.parametrize("n", [1000, 30000])
+def test_fresh_instance_matches_oracle_pipeline(gpu, ref, n):
+    # setup generated on the GPU (fixed-base tool), proved on the GPU and by the reference CPU pipeline
+    zkey, wtns, vk = synth.make_complex_circuit(gpu, n, seed=b"fresh%d" % n)
+    proof_ref, public = G.prove(ref, pkg.bindings, zkey, wtns, FIXED_R, FIXED_S)
+    assert G.verify(ref, proof_ref, public, vk)  # also validates the GPU-generated setup
+    cache = pkg.ZKeyCache(gpu, zkey)
+    try:
+        p, tm = cache.prove(wtns_words(wtns), FIXED_R, FIXED_S)
+        assert pkg.proof_json(p) == G.proof_json(proof_ref)
+        assert tm.total_ms > 0
+    finally:
+        cache.close()
+
+
+def test_sharded_partials_fold_to_the_same_proof(gpu):
+    # SURVEY 8e on one device: 3 "ranks" hold contiguous shards; partial sums folded by finish()
+    zkey, wtns, vk, gold11, goldrs, _ = load(100)
+    w = wtns_words(wtns)
+    caches = [pkg.ZKeyCache(gpu, zkey, rank=r, world=3) for r in range(3)]
+    try:
+        parts = [c.commit_partials(w)[0] for c in caches]
+        proof = caches[0].finish(parts, FIXED_R, FIXED_S)
+        assert pkg.proof_json(proof) == goldrs
+        with pytest.raises(pkg.IcicleError):
+            caches[1].prove(w, 1, 1)  # a sharded cache cannot prove alone
+    finally:
+        for c in caches:
+            c.close()
+
+
+def test_fixed_base_tool_against_reference(gpu, ref, rng):
+    from util import rand_scalars
+    k, _ = rand_scalars(rng, 50)
+    k[0] = 0
+    for g2 in (False, True):
+        pts = synth.fixed_base(gpu, k, g2=g2)
+        std = ref.convert_montgomery(pts, False, kind="g2_affine" if g2 else "affine")
+        gen = ref.generator(g2=g2)
+        for i in range(50):
+            assert np.array_equal(std[i], ref.to_affine(ref.mul_scalar(gen, k[i], g2=g2), g2=g2)), (g2, i)
+
+
+def test_msm_known_dlog_at_scale(gpu, rng):
+    # P_i = k_i G  =>  MSM(s, P) == (sum s_i k_i mod r) G, at a size the CPU oracle is slow at
+    from util import R, array_to_ints, ints_to_array, rand_scalars
+    n = 1 << 20
+    k, kv = rand_scalars(rng, n)
+    s, sv = rand_scalars(rng, n)
+    pts = synth.fixed_base(gpu, k)  # Montgomery
+    cfg = pkg.MSMConfig.default()
+    cfg.are_points_montgomery_form = True
+    got = gpu.msm(s, pts, cfg)[0]
+    dot = sum(a * b for a, b in zip(sv, kv)) % R
+    want = gpu.mul_scalar(gpu.generator(), ints_to_array([dot])[0])
+    assert np.array_equal(gpu.to_affine(got), gpu.to_affine(want))
