@@ -407,6 +407,14 @@ namespace b200 {
     G1Projective *r_b1 = r_a + 1, *r_c = r_a + 2, *r_h = r_a + 3;
     G2Projective* r_b2 = (G2Projective*)(c->d_results + 4 * 96);
 
+    // CacheManager::get_cache re-initialises the NTT domain on every proof (cache.rs:242-256): a no-op unless
+    // someone released or shrank it in between
+    {
+      const NttDomain* d = ntt_domain();
+      if (d && d->max_log < (int)c->power) bn254_ntt_release_domain();
+      if (!d || d->max_log < (int)c->power) B200_TRY(ntt_init_domain_host(host_omega((int)c->power), c->s_copy));
+    }
+
     // witness H2D (proof_helper.rs:194-196); everything else waits on it
     B200_CUDA(cudaEventRecord(c->ev_start, c->s_copy), ICICLE_UNKNOWN_FALLBACK);
     B200_CUDA(

@@ -101,6 +101,7 @@ def make_complex_circuit(backend, n, seed=b"icicle-snark-b200", a=3, log=None):
     tau, alpha, beta, gamma, delta = (tw[k] for k in ("tau", "alpha", "beta", "gamma", "delta"))
     dinv, ginv = pow(delta, -1, R), pow(gamma, -1, R)
 
+    backend.ntt_release_domain()  # init is a no-op when a (possibly smaller) domain already exists
     backend.ntt_init_domain(backend.get_root_of_unity(2 * N))
     try:
         say("lagrange N")
