@@ -40,3 +40,4 @@ def lib() -> IcicleLib:
     return _lib
 
 from .prover import CacheManager, ZKeyCache, groth16_prove, proof_json, proof_to_dict  # noqa: E402,F401
+from . import multi_gpu  # noqa: E402,F401

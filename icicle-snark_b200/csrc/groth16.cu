@@ -418,7 +418,7 @@ namespace b200 {
     // witness H2D (proof_helper.rs:194-196); everything else waits on it
     B200_CUDA(cudaEventRecord(c->ev_start, c->s_copy), ICICLE_UNKNOWN_FALLBACK);
     B200_CUDA(
-      cudaMemcpyAsync(c->d_witness, witness, (size_t)c->n_vars * 32, cudaMemcpyHostToDevice, c->s_copy), ICICLE_COPY_FAILED);
+      cudaMemcpyAsync(c->d_witness, witness, (size_t)c->n_vars * 32, cudaMemcpyDefault, c->s_copy), ICICLE_COPY_FAILED);
     B200_CUDA(cudaEventRecord(c->ev_h2d, c->s_copy), ICICLE_UNKNOWN_FALLBACK);
     for (cudaStream_t s : {c->s_g1, c->s_g2, c->s_q})
       B200_CUDA(cudaStreamWaitEvent(s, c->ev_h2d, 0), ICICLE_UNKNOWN_FALLBACK);

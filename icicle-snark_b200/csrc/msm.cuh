@@ -53,5 +53,7 @@ namespace b200 {
 
   // kernel launches issued by this library since load (bench.py's gpu_launches claim)
   extern unsigned long long g_launches;
+  // optional CUDA events recorded around the accumulate kernel of the next MSM (b200_profile_accumulate)
+  extern cudaEvent_t g_profile_events[2];
 
 } // namespace b200

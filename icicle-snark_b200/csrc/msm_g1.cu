@@ -5,6 +5,7 @@
 namespace b200 {
 
   unsigned long long g_launches = 0;
+  cudaEvent_t g_profile_events[2] = {nullptr, nullptr};
 
   MsmPlan make_msm_plan(int n, int c_req, int bitsize, int factor, bool g2)
   {
@@ -62,5 +63,24 @@ eIcicleError bn254_msm_precompute_bases(
 }
 
 unsigned long long b200_launch_count(void) { return g_launches; }
+
+// enable != 0: record CUDA events around the bucket-accumulation kernel of subsequent MSMs (single stream use);
+// enable == 0: stop. Returns the duration in ms of the last recorded accumulate launch, or -1.
+float b200_profile_accumulate(int enable)
+{
+  float ms = -1.f;
+  if (g_profile_events[0] && g_profile_events[1]) {
+    if (cudaEventSynchronize(g_profile_events[1]) == cudaSuccess) cudaEventElapsedTime(&ms, g_profile_events[0], g_profile_events[1]);
+  }
+  if (enable && !g_profile_events[0]) {
+    cudaEventCreate(&g_profile_events[0]);
+    cudaEventCreate(&g_profile_events[1]);
+  } else if (!enable && g_profile_events[0]) {
+    cudaEventDestroy(g_profile_events[0]);
+    cudaEventDestroy(g_profile_events[1]);
+    g_profile_events[0] = g_profile_events[1] = nullptr;
+  }
+  return ms;
+}
 
 } // extern "C"

@@ -540,9 +540,11 @@ namespace b200 {
       multi_count);
     exclusive_scan(len_hist, plan.item_cap + 1, len_off, tiles, st);
     B200_LAUNCH(msm_item_sort_kernel, grid_for(max_items, 256, 8), 256, 0, st, items, item_off + nb, plan.item_cap, len_off, sorted);
+    if (g_profile_events[0]) cudaEventRecord(g_profile_events[0], st);
     B200_LAUNCH(
       msm_accumulate_kernel<F>, grid_for(max_items, 128, 16), 128, 0, st, sorted, item_off + nb, entries, bases, buckets,
       partials);
+    if (g_profile_events[1]) cudaEventRecord(g_profile_events[1], st);
     B200_LAUNCH(
       msm_fold_kernel<F>, sms, FOLD_BLOCK, FOLD_BLOCK * sizeof(XYZZ<F>), st, multi, multi_count, item_off, partials, buckets);
     B200_LAUNCH(

@@ -296,6 +296,9 @@ double b200_pipe_peak(int mode);
 double b200_imad_peak(int wide);
 /* kernel launches issued by this library since load (bench.py's gpu_launches) */
 unsigned long long b200_launch_count(void);
+/* CUDA-event timing of the MSM bucket-accumulation kernel (the dominant kernel) for bench.py's roofline:
+ * enable/disable recording; returns the last recorded launch's duration in ms (or -1). */
+float b200_profile_accumulate(int enable);
 
 /* library identification: returns a static string "icicle-snark-b200 <version> sm_100a" */
 const char* b200_version(void);

@@ -123,6 +123,13 @@ class ZKeyCacheRef:
         # get_cache: domain from get_root_of_unity (sized by domain_size here: SURVEY App. C)
         self.root = ref.get_root_of_unity(z["domain_size"])
 
+    def get_cache(self):
+        """cache.rs:242-256: (re)initialise the process-wide NTT domain when the zkey changes."""
+        if getattr(self.ref, "domain_root", None) != self.root.tobytes():
+            self.ref.ntt_release_domain()
+            self.ref.ntt_init_domain(self.root)
+        return self
+
 
 def construct_r1cs(ref, cache: ZKeyCacheRef, witness: np.ndarray, B):
     """proof_helper.rs:31-170, same buffers and call order; returns d_vec (3N, 8)."""
@@ -130,26 +137,26 @@ def construct_r1cs(ref, cache: ZKeyCacheRef, witness: np.ndarray, B):
     N = z["domain_size"]
     second = ref.convert_montgomery(np.ascontiguousarray(witness[z["s"]]), False)  # from_mont on the gathered witness
     res = ref.vector_mul(cache.first_slice, second)
-    out = [0] * (2 * N)
-    res_int = [int.from_bytes(res[i].tobytes(), "little") for i in range(len(res))]
-    for i, v in enumerate(res_int):  # the host scatter loop (:81-92)
-        idx = int(z["c"][i]) + int(z["m"][i]) * N
-        out[idx] = (out[idx] + v) % R
-    buf = np.frombuffer(b"".join(v.to_bytes(32, "little") for v in out), dtype=np.uint32).reshape(-1, 8)
+    idx = z["c"] + z["m"] * N
+    buf = np.zeros((2 * N, 8), dtype=np.uint32)
+    if len(np.unique(idx)) == len(idx):  # no collisions: the scatter loop (:81-92) is a plain assignment
+        buf[idx] = res
+    else:
+        out = [0] * (2 * N)
+        res_int = [int.from_bytes(res[i].tobytes(), "little") for i in range(len(res))]
+        for i, v in enumerate(res_int):  # the host scatter loop (:81-92), collisions add mod r
+            out[int(idx[i])] = (out[int(idx[i])] + v) % R
+        buf = np.frombuffer(b"".join(v.to_bytes(32, "little") for v in out), dtype=np.uint32).reshape(-1, 8)
     d = np.zeros((3 * N, 8), dtype=np.uint32)
     d[0:N] = buf[N:]
     d[N:2 * N] = buf[:N]
     d[2 * N:] = ref.vector_mul(np.ascontiguousarray(d[0:N]), np.ascontiguousarray(d[N:2 * N]))
     cfg = B.NTTConfig.default()
     cfg.batch_size = 3
-    ref.ntt_init_domain(cache.root)
-    try:
-        d = ref.ntt(d, B.kInverse, cfg)
-        for k in range(3):
-            d[k * N:(k + 1) * N] = ref.vector_mul(np.ascontiguousarray(d[k * N:(k + 1) * N]), cache.keys)
-        d = ref.ntt(d, B.kForward, cfg)
-    finally:
-        ref.ntt_release_domain()
+    d = ref.ntt(d, B.kInverse, cfg)
+    for k in range(3):
+        d[k * N:(k + 1) * N] = ref.vector_mul(np.ascontiguousarray(d[k * N:(k + 1) * N]), cache.keys)
+    d = ref.ntt(d, B.kForward, cfg)
     d[0:N] = ref.vector_mul(np.ascontiguousarray(d[0:N]), np.ascontiguousarray(d[N:2 * N]))
     d[N:2 * N] = ref.vector_sub(np.ascontiguousarray(d[0:N]), np.ascontiguousarray(d[2 * N:]))
     return d
@@ -172,6 +179,8 @@ def prove(ref, B, zkey_bytes, wtns_bytes, r: int, s: int, cache: ZKeyCacheRef | 
     """groth16_prove_helper with injected blinding factors (r = s = 1 is the `no-randomness` feature)."""
     cache = cache or ZKeyCacheRef(ref, zkey_bytes)
     z = cache.z
+    if hasattr(cache, "get_cache"):
+        cache.get_cache()
     w = parse_wtns(wtns_bytes)
     if w["q"] != FR_BYTES:
         raise ValueError("Curve of the witness does not match the curve of the proving key")

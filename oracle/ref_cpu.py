@@ -37,7 +37,21 @@ def ref():
         pkg = sys.modules.get("icicle_snark_b200")
         if pkg is None:
             raise RuntimeError("load the icicle_snark_b200 package first (tests/conftest.py does)")
-        r = pkg.IcicleLib(REF_LIB)
+        class RefLib(pkg.IcicleLib):
+            """Tracks the process-wide NTT domain so callers can tell which root is live
+            (initialising an existing domain is a no-op in the reference, ntt.cuh:452)."""
+            domain_root = None
+
+            def ntt_init_domain(self, root):
+                super().ntt_init_domain(root)
+                if self.domain_root is None:
+                    self.domain_root = bytes(memoryview(root).tobytes())
+
+            def ntt_release_domain(self):
+                super().ntt_release_domain()
+                self.domain_root = None
+
+        r = RefLib(REF_LIB)
         r.set_device("CPU", 0)
         _ref = r
     return _ref
