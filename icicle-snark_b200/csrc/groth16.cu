@@ -306,9 +306,7 @@ namespace b200 {
     shard(n_c, rank, world, &c->c_lo, &c->c_hi);
     shard(N, rank, world, &c->h_lo, &c->h_hi);
     auto plan_for = [&](uint32_t n, bool g2) {
-      MsmPlan pl = make_msm_plan(n ? (int)n : 1, 0, 254, 1, g2);
-      if (c->precompute > 1) pl = make_msm_plan(n ? (int)n : 1, pl.c, 254, c->precompute, g2);
-      return pl;
+      return make_msm_plan(n ? (int)n : 1, 0, 254, c->precompute, g2);
     };
     c->planA = plan_for(c->a_hi - c->a_lo, false);
     c->planC = plan_for(c->c_hi - c->c_lo, false);

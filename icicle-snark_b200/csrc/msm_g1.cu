@@ -20,6 +20,11 @@ namespace b200 {
       while ((1ll << lg) < n) ++lg;
       c = lg - 5;
       if (g2) c -= 1;
+      // every window folded into one bucket set by precomputed bases: the reduction is 1/W of the work,
+      // so wider windows (fewer adds per scalar) pay
+      if (c < 2) c = 2;
+      int w0 = (bitsize + 2 + c - 1) / c;
+      if (factor >= w0 && w0 > 1 && lg >= 12) c = lg - 1 < 21 ? lg - 1 : 21;
     }
     if (c < 2) c = 2;
     if (c > 22) c = 22;

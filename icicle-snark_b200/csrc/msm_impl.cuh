@@ -343,8 +343,26 @@ namespace b200 {
   }
 
   static constexpr int FOLD_BLOCK = 64;
+  static constexpr uint32_t FOLD_SERIAL_MAX = 32; // buckets cut into <= this many items are folded by one thread
 
-  // (5b) buckets that were cut into several items: one CTA folds the partial sums
+  // (5b) buckets that were cut into several items. Moderately long buckets (the common case when one bucket
+  // set serves all windows) are folded by one thread each; giant ones (skewed scalars) by one CTA each.
+  template <class F>
+  __global__ void __launch_bounds__(128) msm_fold_serial_kernel(
+    const uint32_t* multi, const uint32_t* multi_count, const uint32_t* item_off, const XYZZ<F>* partials, XYZZ<F>* buckets)
+  {
+    uint32_t nm = *multi_count;
+    for (uint32_t m = blockIdx.x * blockDim.x + threadIdx.x; m < nm; m += gridDim.x * blockDim.x) {
+      uint32_t k = multi[m];
+      uint32_t first = item_off[k], ni = item_off[k + 1] - first;
+      if (ni > FOLD_SERIAL_MAX) continue;
+      XYZZ<F> acc = ld_struct(partials + first);
+      for (uint32_t j = 1; j < ni; ++j)
+        xyzz_add_ni(acc, ld_struct(partials + first + j));
+      st_struct(buckets + k, acc);
+    }
+  }
+
   template <class F>
   __global__ void __launch_bounds__(FOLD_BLOCK) msm_fold_kernel(
     const uint32_t* multi, const uint32_t* multi_count, const uint32_t* item_off, const XYZZ<F>* partials, XYZZ<F>* buckets)
@@ -355,6 +373,7 @@ namespace b200 {
     for (uint32_t m = blockIdx.x; m < nm; m += gridDim.x) {
       uint32_t k = multi[m];
       uint32_t first = item_off[k], ni = item_off[k + 1] - first;
+      if (ni <= FOLD_SERIAL_MAX) continue; // uniform per CTA
       XYZZ<F> r = block_sum<F, FOLD_BLOCK>(partials + first, ni, sh);
       if (threadIdx.x == 0) st_struct(buckets + k, r);
       __syncthreads();
@@ -545,6 +564,7 @@ namespace b200 {
       msm_accumulate_kernel<F>, grid_for(max_items, 128, 16), 128, 0, st, sorted, item_off + nb, entries, bases, buckets,
       partials);
     if (g_profile_events[1]) cudaEventRecord(g_profile_events[1], st);
+    B200_LAUNCH(msm_fold_serial_kernel<F>, grid_for(nb, 128, 8), 128, 0, st, multi, multi_count, item_off, partials, buckets);
     B200_LAUNCH(
       msm_fold_kernel<F>, sms, FOLD_BLOCK, FOLD_BLOCK * sizeof(XYZZ<F>), st, multi, multi_count, item_off, partials, buckets);
     B200_LAUNCH(

@@ -221,6 +221,8 @@ def test_msm_all_zero_and_empty(gpu, ref, rng):
 def domains(gpu, ref):
     root = ref.get_root_of_unity(1 << 20)
     assert np.array_equal(root, gpu.get_root_of_unity(1 << 20))
+    gpu.ntt_release_domain()  # initialising over an existing (smaller) domain is a no-op, as in the reference
+    ref.ntt_release_domain()
     gpu.ntt_init_domain(root)
     ref.ntt_init_domain(root)
     yield 20
