@@ -25,6 +25,13 @@ namespace b200 {
       if (c < 2) c = 2;
       int w0 = (bitsize + 2 + c - 1) / c;
       if (factor >= w0 && w0 > 1 && lg >= 12) c = lg - 1 < 21 ? lg - 1 : 21;
+      // a top window holding only 1..4 bits of the scalar funnels n/2^bits entries into each of a few
+      // buckets; step down until the top window is either empty or reasonably wide
+      while (c > 2) {
+        int w = (bitsize + 2 + c - 1) / c;
+        int top_bits = bitsize - c * (w - 1);
+        if (top_bits > 0 && top_bits <= 4) --c; else break;
+      }
     }
     if (c < 2) c = 2;
     if (c > 22) c = 22;

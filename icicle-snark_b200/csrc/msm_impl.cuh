@@ -87,8 +87,11 @@ namespace b200 {
   {
     const uint32_t half = 1u << (pl.c - 1);
     const uint32_t mask = (1u << pl.c) - 1;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < pl.n; i += gridDim.x * blockDim.x) {
-      Fr s = ld_fr(scalars + i);
+    const int lane = threadIdx.x & 31;
+    const int n_round = (pl.n + 31) & ~31; // whole warps stay in the loop so the warp-wide match below is convergent
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += gridDim.x * blockDim.x) {
+      const bool live = i < pl.n;
+      Fr s = live ? ld_fr(scalars + i) : Fr::zero();
       if (scalars_mont) s = Fr::from_mont(s);
       uint32_t t[10];
       uint64_t carry = 0;
@@ -105,14 +108,18 @@ namespace b200 {
         int limb = bit >> 5, sh = bit & 31;
         uint64_t two = ((uint64_t)t[limb + 1] << 32) | t[limb];
         uint32_t u = (uint32_t)(two >> sh) & mask;
-        uint32_t out = DIGIT_NONE;
-        if (u != half) {
+        uint32_t out = DIGIT_NONE, key = DIGIT_NONE;
+        if (live && u != half) {
           uint32_t neg = u < half;
           uint32_t mag = neg ? half - u : u - half; // 1..half
           out = (mag - 1) | (neg << 31);
-          atomicAdd(&hist[(w % pl.sets) * pl.bpw + (mag - 1)], 1u);
+          key = (w % pl.sets) * pl.bpw + (mag - 1);
         }
-        digits[(size_t)w * pl.n + i] = out;
+        // warp-aggregated histogram: skewed scalars (0/1-heavy witnesses) and short top windows put
+        // millions of entries on a handful of keys; one atomic per distinct key per warp
+        uint32_t peers = __match_any_sync(0xffffffffu, key);
+        if (key != DIGIT_NONE && lane == __ffs(peers) - 1) atomicAdd(&hist[key], (uint32_t)__popc(peers));
+        if (live) digits[(size_t)w * pl.n + i] = out;
       }
     }
   }
@@ -221,14 +228,23 @@ namespace b200 {
   static __global__ void __launch_bounds__(256)
     msm_scatter_kernel(MsmDev pl, const uint32_t* digits, uint32_t* cursor, uint32_t* entries)
   {
-    size_t total = (size_t)pl.n * pl.windows;
-    for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
-      uint32_t d = digits[e];
-      if (d == DIGIT_NONE) continue;
+    const size_t total = (size_t)pl.n * pl.windows;
+    const size_t total_round = (total + 31) & ~(size_t)31;
+    const int lane = threadIdx.x & 31;
+    for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < total_round; e += (size_t)gridDim.x * blockDim.x) {
+      uint32_t d = e < total ? digits[e] : DIGIT_NONE;
       int w = (int)(e / pl.n), i = (int)(e - (size_t)w * pl.n);
-      uint32_t key = (w % pl.sets) * pl.bpw + (d & 0x7fffffffu);
-      uint32_t pos = atomicAdd(&cursor[key], 1u);
-      entries[pos] = (uint32_t)(i * pl.factor + w / pl.sets) | (d & 0x80000000u);
+      uint32_t key = d == DIGIT_NONE ? DIGIT_NONE : (w % pl.sets) * pl.bpw + (d & 0x7fffffffu);
+      // warp-aggregated cursor bump: the leader of each group of equal keys reserves the whole run
+      uint32_t peers = __match_any_sync(0xffffffffu, key);
+      int leader = __ffs(peers) - 1;
+      uint32_t base = 0;
+      if (key != DIGIT_NONE && lane == leader) base = atomicAdd(&cursor[key], (uint32_t)__popc(peers));
+      base = __shfl_sync(0xffffffffu, base, leader);
+      if (key != DIGIT_NONE) {
+        uint32_t pos = base + __popc(peers & ((1u << lane) - 1));
+        entries[pos] = (uint32_t)(i * pl.factor + w / pl.sets) | (d & 0x80000000u);
+      }
     }
   }
 
@@ -414,15 +430,19 @@ namespace b200 {
 
   static constexpr int WSUM_BLOCK = 128;
 
+  // sums `per_cta` consecutive values per CTA: in[set][g*per_cta ..] -> out[set*gridDim.x + g]; two levels of this
+  // reduce the chunk sums of a set to one value without a single long serial loop
   template <class F>
-  __global__ void __launch_bounds__(WSUM_BLOCK) msm_set_sum_kernel(MsmDev pl, const XYZZ<F>* chunk_sums, XYZZ<F>* set_sums)
+  __global__ void __launch_bounds__(WSUM_BLOCK)
+    msm_set_sum_kernel(const XYZZ<F>* in, int per_set, int per_cta, XYZZ<F>* out)
   {
     extern __shared__ uint4 smem_raw[];
     XYZZ<F>* sh = reinterpret_cast<XYZZ<F>*>(smem_raw);
-    int chunks_per_set = pl.bpw / REDUCE_CHUNK;
-    if (chunks_per_set == 0) chunks_per_set = 1;
-    XYZZ<F> r = block_sum<F, WSUM_BLOCK>(chunk_sums + (size_t)blockIdx.x * chunks_per_set, chunks_per_set, sh);
-    if (threadIdx.x == 0) st_struct(set_sums + blockIdx.x, r);
+    int beg = blockIdx.x * per_cta;
+    int cnt = per_set - beg < per_cta ? per_set - beg : per_cta;
+    if (cnt < 0) cnt = 0;
+    XYZZ<F> r = block_sum<F, WSUM_BLOCK>(in + (size_t)blockIdx.y * per_set + beg, (uint32_t)cnt, sh);
+    if (threadIdx.x == 0) st_struct(out + (size_t)blockIdx.y * gridDim.x + blockIdx.x, r);
   }
 
   // Horner over sets (weights 2^(c*set)); writes the reference's boundary layout
@@ -569,7 +589,20 @@ namespace b200 {
       msm_fold_kernel<F>, sms, FOLD_BLOCK, FOLD_BLOCK * sizeof(XYZZ<F>), st, multi, multi_count, item_off, partials, buckets);
     B200_LAUNCH(
       msm_reduce_chunks_kernel<F>, grid_for((size_t)plan.sets * chunks_per_set, 128, 16), 128, 0, st, pl, buckets, chunk_sums);
-    B200_LAUNCH(msm_set_sum_kernel<F>, plan.sets, WSUM_BLOCK, WSUM_BLOCK * sizeof(XYZZ<F>), st, pl, chunk_sums, set_sums);
+    {
+      // level 1: G CTAs per set, level 2: one CTA per set over the G partial sums
+      int G = (chunks_per_set + WSUM_BLOCK * 4 - 1) / (WSUM_BLOCK * 4);
+      if (G > 128) G = 128;
+      if (G < 1) G = 1;
+      int per_cta = (chunks_per_set + G - 1) / G;
+      const size_t sm = WSUM_BLOCK * sizeof(XYZZ<F>);
+      if (G == 1) {
+        B200_LAUNCH(msm_set_sum_kernel<F>, dim3(1, plan.sets), WSUM_BLOCK, sm, st, chunk_sums, chunks_per_set, chunks_per_set, set_sums);
+      } else {
+        B200_LAUNCH(msm_set_sum_kernel<F>, dim3(G, plan.sets), WSUM_BLOCK, sm, st, chunk_sums, chunks_per_set, per_cta, partials);
+        B200_LAUNCH(msm_set_sum_kernel<F>, dim3(1, plan.sets), WSUM_BLOCK, sm, st, partials, G, G, set_sums);
+      }
+    }
     B200_LAUNCH(msm_final_kernel<F>, 1, 32, 0, st, pl, set_sums, out_std);
     chk(cudaGetLastError());
     cudaFreeAsync(base, st);
