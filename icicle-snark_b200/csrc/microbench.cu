@@ -5,6 +5,7 @@
 //   mode 4: 4 IMAD.WIDE chains + 4 DFMA chains interleaved (do the two pipes issue concurrently?)
 //   mode 5: mad.lo.cc/madc.hi pairs as the field multiplier emits them (IMAD.WIDE.U32.X carry chains)
 #include "common.cuh"
+#include "field.cuh"
 
 namespace b200 {
 
@@ -103,6 +104,88 @@ namespace b200 {
     if (sink == 0x123456789abcdefull) out[0] = sink;
   }
 
+  // ---- field-multiplier candidates (throughput of dependent Montgomery products, 4 chains per thread)
+  // mode 6: the production 8x32-bit CIOS (carry chains, IMAD.WIDE.X); mode 7: 9x29-bit limbs with plain
+  // IMAD.WIDE column accumulation (no carry-in), lazy carries.
+  struct F29 {
+    uint32_t v[9];
+  };
+  __device__ __forceinline__ F29 mul29(const F29& a, const F29& b)
+  {
+    constexpr uint32_t MASK = (1u << 29) - 1, PINV = 0x4866389u;
+    constexpr uint32_t PL[9] = {0x187cfd47, 0x10460b6, 0x1c72a34f, 0x2d522d0, 0x1585d978, 0x2db40c0, 0xa6e141, 0xe5c2634, 0x30644e};
+    uint64_t c[18];
+#pragma unroll
+    for (int k = 0; k < 18; ++k)
+      c[k] = 0;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) {
+#pragma unroll
+      for (int j = 0; j < 9; ++j)
+        c[i + j] += (uint64_t)a.v[j] * b.v[i];
+      uint32_t m = ((uint32_t)c[i] * PINV) & MASK;
+#pragma unroll
+      for (int j = 0; j < 9; ++j)
+        c[i + j] += (uint64_t)m * PL[j];
+      c[i + 1] += c[i] >> 29;
+    }
+    F29 r;
+    uint64_t carry = 0;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+      uint64_t v = c[9 + k] + carry;
+      r.v[k] = k < 8 ? (uint32_t)v & MASK : (uint32_t)v;
+      carry = v >> 29;
+    }
+    return r;
+  }
+
+  template <int MODE>
+  __global__ void __launch_bounds__(128) fieldmul_kernel(uint32_t* out, int iters, uint32_t seed)
+  {
+    if (MODE == 6) {
+      Fq x[4], y;
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          x[k].v[i] = (threadIdx.x * 2654435761u + seed + i * 40503u + k) & 0x0fffffffu;
+      y = x[0];
+      for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          x[k] = x[k] * y;
+      }
+      uint32_t s = 0;
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          s ^= x[k].v[i];
+      if (s == 0x12345678u) out[0] = s;
+    } else {
+      F29 x[4], y;
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+#pragma unroll
+        for (int i = 0; i < 9; ++i)
+          x[k].v[i] = (threadIdx.x * 2654435761u + seed + i * 40503u + k) & 0x0fffffffu;
+      y = x[0];
+      for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          x[k] = mul29(x[k], y);
+      }
+      uint32_t s = 0;
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+#pragma unroll
+        for (int i = 0; i < 9; ++i)
+          s ^= x[k].v[i];
+      if (s == 0x12345678u) out[0] = s;
+    }
+  }
+
   template <int MODE>
   static void launch_pipe(uint64_t* d, int iters, int blocks, int rep)
   {
@@ -126,6 +209,20 @@ extern "C" double b200_pipe_peak(int mode)
   double best = -1.0;
   for (int rep = 0; rep < 5; ++rep) {
     cudaEventRecord(e0, 0);
+    if (mode >= 6) {
+      const int it2 = 512, bl2 = sm_count() * 8;
+      if (mode == 6)
+        fieldmul_kernel<6><<<bl2, 128>>>((uint32_t*)d, it2, rep);
+      else
+        fieldmul_kernel<7><<<bl2, 128>>>((uint32_t*)d, it2, rep);
+      cudaEventRecord(e1, 0);
+      if (cudaEventSynchronize(e1) != cudaSuccess) break;
+      float ms2 = 0;
+      cudaEventElapsedTime(&ms2, e0, e1);
+      double rate2 = (double)bl2 * 128 * it2 * 4 / (ms2 * 1e-3); // field products per second
+      if (rate2 > best) best = rate2;
+      continue;
+    }
     switch (mode) {
     case 0: launch_pipe<0>(d, iters, blocks, rep); break;
     case 1: launch_pipe<1>(d, iters, blocks, rep); break;

@@ -309,7 +309,18 @@ namespace b200 {
   // next point prefetched into registers while the current add runs. Hot loop #1
   // (replaces accumulate_buckets_kernel, cuda_msm.cuh:223-255).
   template <class F>
-  __global__ void __launch_bounds__(128) msm_accumulate_kernel(
+  struct AccTraits { // G1: 128 registers, next point prefetched into registers
+    static constexpr bool kPrefetch = true;
+    static constexpr int kMinBlocks = 4;
+  };
+  template <>
+  struct AccTraits<Fq2> { // G2: the accumulator alone is 64 registers; no register prefetch, 3 CTAs/SM instead
+    static constexpr bool kPrefetch = false;
+    static constexpr int kMinBlocks = 3;
+  };
+
+  template <class F>
+  __global__ void __launch_bounds__(128, AccTraits<F>::kMinBlocks) msm_accumulate_kernel(
     const MsmItem* sorted, const uint32_t* total_items, const uint32_t* entries, const Affine<F>* bases, XYZZ<F>* buckets,
     XYZZ<F>* partials)
   {
@@ -319,19 +330,30 @@ namespace b200 {
       const uint32_t* e = entries + it.x;
       uint32_t len = it.y;
       XYZZ<F> acc = XYZZ<F>::inf();
-      uint32_t cur = e[0];
-      Affine<F> p = ld_affine(bases + (cur & 0x7fffffffu));
-      for (uint32_t k = 0; k < len; ++k) {
-        uint32_t nxt = cur;
-        Affine<F> pn = p;
-        if (k + 1 < len) {
-          nxt = e[k + 1];
-          pn = ld_affine(bases + (nxt & 0x7fffffffu));
+      if (AccTraits<F>::kPrefetch) {
+        uint32_t cur = e[0];
+        Affine<F> p = ld_affine(bases + (cur & 0x7fffffffu));
+        for (uint32_t k = 0; k < len; ++k) {
+          uint32_t nxt = cur;
+          Affine<F> pn = p;
+          if (k + 1 < len) {
+            nxt = e[k + 1];
+            pn = ld_affine(bases + (nxt & 0x7fffffffu));
+          }
+          if (cur >> 31) p.y = p.y.neg();
+          acc.madd(p);
+          cur = nxt;
+          p = pn;
         }
-        if (cur >> 31) p.y = p.y.neg();
-        acc.madd(p);
-        cur = nxt;
-        p = pn;
+      } else {
+        uint32_t cur = e[0];
+        for (uint32_t k = 0; k < len; ++k) {
+          Affine<F> p = ld_affine(bases + (cur & 0x7fffffffu));
+          uint32_t sign = cur >> 31;
+          if (k + 1 < len) cur = e[k + 1];
+          if (sign) p.y = p.y.neg();
+          acc.madd(p);
+        }
       }
       XYZZ<F>* dst = (it.w >> 31) ? partials + (it.w & 0x7fffffffu) : buckets + it.w;
       st_struct(dst, acc);
