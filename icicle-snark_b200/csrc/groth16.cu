@@ -16,8 +16,9 @@
 //     crosses PCIe twice and scatters in a single-thread loop, proof_helper.rs:55-99).
 //   * iNTT -> x keys -> NTT runs on the Stockham passes of ntt.cu with 1/N * keys fused into the last
 //     iNTT pass; A'.B' - C' and the conversion to standard form are one kernel.
-//   * A, B1, C, B2 start as soon as the witness is on the device, concurrently with the quotient chain;
-//     H follows on the chain's stream.  Four streams, no host synchronisation until the five results.
+//   * A, B1, C, B2 start as soon as the witness is on the device, each on its own stream, concurrently with the
+//     quotient chain; H follows on the chain's (higher-priority) stream.  No host synchronisation until the
+//     five results are back.
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
@@ -154,9 +155,9 @@ struct b200_zkey_cache {
   Fr *d_witness = nullptr, *d_vec = nullptr, *d_h = nullptr;
   uint8_t* d_results = nullptr; // 4 x G1 projective + 1 x G2 projective
   uint8_t* h_results = nullptr; // pinned
-  cudaStream_t s_copy = nullptr, s_g1 = nullptr, s_g2 = nullptr, s_q = nullptr;
+  cudaStream_t s_copy = nullptr, s_g1 = nullptr, s_b1 = nullptr, s_c = nullptr, s_g2 = nullptr, s_q = nullptr;
   cudaEvent_t ev_wit = nullptr, ev_start = nullptr, ev_h2d = nullptr, ev_r1cs = nullptr, ev_ntt = nullptr, ev_g1 = nullptr,
-              ev_g2 = nullptr, ev_q = nullptr, ev_prev = nullptr;
+              ev_g2 = nullptr, ev_q = nullptr, ev_prev = nullptr, ev_b1 = nullptr, ev_c = nullptr;
   std::mutex mu;
 };
 
@@ -186,10 +187,10 @@ namespace b200 {
     for (void* p : ptrs)
       if (p) cudaFree(p);
     if (c->h_results) cudaFreeHost(c->h_results);
-    cudaStream_t ss[] = {c->s_copy, c->s_g1, c->s_g2, c->s_q};
+    cudaStream_t ss[] = {c->s_copy, c->s_g1, c->s_b1, c->s_c, c->s_g2, c->s_q};
     for (auto s : ss)
       if (s) cudaStreamDestroy(s);
-    cudaEvent_t es[] = {c->ev_wit, c->ev_start, c->ev_h2d, c->ev_r1cs, c->ev_ntt, c->ev_g1, c->ev_g2, c->ev_q, c->ev_prev};
+    cudaEvent_t es[] = {c->ev_wit, c->ev_start, c->ev_h2d, c->ev_r1cs, c->ev_ntt, c->ev_g1, c->ev_g2, c->ev_q, c->ev_prev, c->ev_b1, c->ev_c};
     for (auto e : es)
       if (e) cudaEventDestroy(e);
     delete c;
@@ -291,11 +292,19 @@ namespace b200 {
     }                                                                                                                  \
   } while (0)
 
-    CK(cudaStreamCreateWithFlags(&c->s_copy, cudaStreamNonBlocking));
-    CK(cudaStreamCreateWithFlags(&c->s_g1, cudaStreamNonBlocking));
-    CK(cudaStreamCreateWithFlags(&c->s_g2, cudaStreamNonBlocking));
-    CK(cudaStreamCreateWithFlags(&c->s_q, cudaStreamNonBlocking));
-    for (cudaEvent_t* e : {&c->ev_wit, &c->ev_prev})
+    // the quotient chain feeds the H MSM, so its (shared-memory heavy) NTT CTAs get scheduling priority over the
+    // register-hungry accumulate kernels of the witness-only MSMs; G2 (the longest single MSM) comes next
+    int prio_lo = 0, prio_hi = 0;
+    CK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi)); // lo = least urgent (numerically greatest)
+    const char* pe = getenv("B200_STREAM_PRIO");
+    const bool use_prio = !(pe && pe[0] == '0');
+    CK(cudaStreamCreateWithPriority(&c->s_copy, cudaStreamNonBlocking, prio_hi));
+    CK(cudaStreamCreateWithPriority(&c->s_q, cudaStreamNonBlocking, use_prio ? prio_hi : prio_lo));
+    CK(cudaStreamCreateWithPriority(&c->s_g2, cudaStreamNonBlocking, use_prio && prio_hi + 1 <= prio_lo ? prio_hi + 1 : prio_lo));
+    CK(cudaStreamCreateWithPriority(&c->s_g1, cudaStreamNonBlocking, prio_lo));
+    CK(cudaStreamCreateWithPriority(&c->s_b1, cudaStreamNonBlocking, prio_lo));
+    CK(cudaStreamCreateWithPriority(&c->s_c, cudaStreamNonBlocking, prio_lo));
+    for (cudaEvent_t* e : {&c->ev_wit, &c->ev_prev, &c->ev_b1, &c->ev_c})
       CK(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
     for (cudaEvent_t* e : {&c->ev_start, &c->ev_h2d, &c->ev_r1cs, &c->ev_ntt, &c->ev_g1, &c->ev_g2, &c->ev_q})
       CK(cudaEventCreate(e));
@@ -418,7 +427,7 @@ namespace b200 {
     B200_CUDA(
       cudaMemcpyAsync(c->d_witness, witness, (size_t)c->n_vars * 32, cudaMemcpyDefault, c->s_copy), ICICLE_COPY_FAILED);
     B200_CUDA(cudaEventRecord(c->ev_h2d, c->s_copy), ICICLE_UNKNOWN_FALLBACK);
-    for (cudaStream_t s : {c->s_g1, c->s_g2, c->s_q})
+    for (cudaStream_t s : {c->s_g1, c->s_b1, c->s_c, c->s_g2, c->s_q})
       B200_CUDA(cudaStreamWaitEvent(s, c->ev_h2d, 0), ICICLE_UNKNOWN_FALLBACK);
 
     // quotient chain + H on s_q
@@ -438,13 +447,18 @@ namespace b200 {
     const Fr* w = c->d_witness;
     if (c->a_hi > c->a_lo) {
       if ((err = msm_enqueue<Fq>(c->planA, w + c->a_lo, false, c->pA, r_a, c->s_g1)) != ICICLE_SUCCESS) return err;
-      if ((err = msm_enqueue<Fq>(c->planA, w + c->a_lo, false, c->pB1, r_b1, c->s_g1)) != ICICLE_SUCCESS) return err;
+      if ((err = msm_enqueue<Fq>(c->planA, w + c->a_lo, false, c->pB1, r_b1, c->s_b1)) != ICICLE_SUCCESS) return err;
       if ((err = msm_enqueue<Fq2>(c->planB2, w + c->a_lo, false, c->pB2, r_b2, c->s_g2)) != ICICLE_SUCCESS) return err;
     }
     if (c->c_hi > c->c_lo) {
-      if ((err = msm_enqueue<Fq>(c->planC, w + c->n_public + 1 + c->c_lo, false, c->pC, r_c, c->s_g1)) != ICICLE_SUCCESS)
+      if ((err = msm_enqueue<Fq>(c->planC, w + c->n_public + 1 + c->c_lo, false, c->pC, r_c, c->s_c)) != ICICLE_SUCCESS)
         return err;
     }
+    // every MSM has its own stream: their latency-bound tails (bucket reduction) overlap other MSMs' accumulation
+    cudaEventRecord(c->ev_b1, c->s_b1);
+    cudaEventRecord(c->ev_c, c->s_c);
+    cudaStreamWaitEvent(c->s_g1, c->ev_b1, 0);
+    cudaStreamWaitEvent(c->s_g1, c->ev_c, 0);
     cudaEventRecord(c->ev_g1, c->s_g1);
     cudaEventRecord(c->ev_g2, c->s_g2);
 
