@@ -291,16 +291,6 @@ namespace b200 {
   typedef Fp<FrCfg> Fr;
   typedef Fp<FqCfg> Fq;
 
-  // Out-of-line base-field product for the Fq2 tower on the device: a G2 mixed add is 28 base products; fully
-  // inlined that is ~80 KB of SASS, which thrashes the 32 KB instruction cache (ncu: stall_no_instruction 1.3 per
-  // issue, fmaheavy 57 % busy). Arguments and result travel in registers (no stack traffic in SASS).
-#ifdef __CUDA_ARCH__
-  __device__ __noinline__ inline Fq fq_mul_call(Fq a, Fq b) { return a * b; }
-#define B200_FQ_MUL(a, b) fq_mul_call(a, b)
-#else
-#define B200_FQ_MUL(a, b) ((a) * (b))
-#endif
-
   // ---------------------------------------------------------------------------------------------
   // Fq2 = Fq[u]/(u^2+1)  (nonresidue -1: /root/reference/icicle/include/icicle/fields/snark_fields/bn254_base.h:67-71;
   // reference product: /root/reference/icicle/include/icicle/fields/complex_extension.h:192-219)
@@ -315,19 +305,42 @@ namespace b200 {
     friend B200_HD Fq2 operator-(const Fq2& a, const Fq2& b) { return {a.c0 - b.c0, a.c1 - b.c1}; }
     B200_HD Fq2 neg() const { return {c0.neg(), c1.neg()}; }
     B200_HD Fq2 dbl() const { return {c0.dbl(), c1.dbl()}; }
+    // Karatsuba: 3 base-field products
+    static B200_HD Fq2 mul_inline(const Fq2& a, const Fq2& b)
+    {
+      Fq t0 = a.c0 * b.c0;
+      Fq t1 = a.c1 * b.c1;
+      Fq t2 = (a.c0 + a.c1) * (b.c0 + b.c1);
+      return {t0 - t1, t2 - t0 - t1};
+    }
+    // (c0+c1)(c0-c1), 2 c0 c1 : 2 base-field products
+    static B200_HD Fq2 sqr_inline(const Fq2& a)
+    {
+      Fq s = a.c0 + a.c1, d = a.c0 - a.c1, m = a.c0 * a.c1;
+      return {s * d, m.dbl()};
+    }
+    // Out-of-line on the device: a G2 mixed add is 8 products + 2 squarings in Fq2 = 28 base products; fully inlined
+    // that is ~80 KB of SASS, which thrashes the 32 KB instruction cache (ncu before the change:
+    // stall_no_instruction 1.3 per issue, fmaheavy 57 % busy). Arguments/result travel in registers.
+#if defined(__CUDACC__)
+    static __device__ __noinline__ Fq2 mul_call(Fq2 a, Fq2 b) { return mul_inline(a, b); }
+    static __device__ __noinline__ Fq2 sqr_call(Fq2 a) { return sqr_inline(a); }
+#endif
     friend B200_HD Fq2 operator*(const Fq2& a, const Fq2& b)
     {
-      // Karatsuba: 3 base-field products
-      Fq t0 = B200_FQ_MUL(a.c0, b.c0);
-      Fq t1 = B200_FQ_MUL(a.c1, b.c1);
-      Fq t2 = B200_FQ_MUL(a.c0 + a.c1, b.c0 + b.c1);
-      return {t0 - t1, t2 - t0 - t1};
+#ifdef __CUDA_ARCH__
+      return mul_call(a, b);
+#else
+      return mul_inline(a, b);
+#endif
     }
     B200_HD Fq2 sqr() const
     {
-      // (c0+c1)(c0-c1), 2 c0 c1 : 2 base-field products
-      Fq s = c0 + c1, d = c0 - c1, m = B200_FQ_MUL(c0, c1);
-      return {B200_FQ_MUL(s, d), m.dbl()};
+#ifdef __CUDA_ARCH__
+      return sqr_call(*this);
+#else
+      return sqr_inline(*this);
+#endif
     }
     static B200_HD Fq2 to_mont(const Fq2& a) { return {Fq::to_mont(a.c0), Fq::to_mont(a.c1)}; }
     static B200_HD Fq2 from_mont(const Fq2& a) { return {Fq::from_mont(a.c0), Fq::from_mont(a.c1)}; }
