@@ -226,38 +226,52 @@ namespace b200 {
       for (int i = 0; i < 8; ++i)
         r.v[i] = bw ? s[i] : t[i];
 #else
-      uint32_t t[10] = {0};
-      for (int i = 0; i < 8; ++i) {
-        uint64_t c = 0;
-        for (int j = 0; j < 8; ++j) {
-          c += (uint64_t)a.v[j] * b.v[i] + t[j];
-          t[j] = (uint32_t)c;
-          c >>= 32;
-        }
-        c += t[8];
-        t[8] = (uint32_t)c;
-        t[9] = (uint32_t)(c >> 32);
-        uint32_t m = t[0] * Cfg::INV;
-        c = ((uint64_t)m * Cfg::P(0) + t[0]) >> 32;
-        for (int j = 1; j < 8; ++j) {
-          c += (uint64_t)m * Cfg::P(j) + t[j];
-          t[j - 1] = (uint32_t)c;
-          c >>= 32;
-        }
-        c += t[8];
-        t[7] = (uint32_t)c;
-        t[8] = t[9] + (uint32_t)(c >> 32);
+      // host: 4x64-bit CIOS on unsigned __int128 (the prover epilogue's ~2.5k products per proof)
+      typedef unsigned __int128 u128;
+      uint64_t A[4], B[4], P[4], t[6] = {0, 0, 0, 0, 0, 0};
+      for (int i = 0; i < 4; ++i) {
+        A[i] = ((uint64_t)a.v[2 * i + 1] << 32) | a.v[2 * i];
+        B[i] = ((uint64_t)b.v[2 * i + 1] << 32) | b.v[2 * i];
+        P[i] = ((uint64_t)Cfg::P(2 * i + 1) << 32) | Cfg::P(2 * i);
       }
-      uint32_t u[8];
-      int64_t bw = 0;
-      for (int i = 0; i < 8; ++i) {
-        int64_t d = (int64_t)t[i] - Cfg::P(i) + bw;
-        u[i] = (uint32_t)d;
-        bw = d >> 32;
+      // -p^-1 mod 2^64 from the 32-bit constant by one Newton step: x' = x (2 - p x); sign handled below
+      uint64_t pinv32 = (uint64_t)(uint32_t)(0u - Cfg::INV); // p^-1 mod 2^32
+      uint64_t pinv64 = pinv32 * (2 - P[0] * pinv32);         // p^-1 mod 2^64
+      uint64_t ninv = 0 - pinv64;                             // -p^-1 mod 2^64
+      for (int i = 0; i < 4; ++i) {
+        u128 c = 0;
+        for (int j = 0; j < 4; ++j) {
+          c += (u128)A[j] * B[i] + t[j];
+          t[j] = (uint64_t)c;
+          c >>= 64;
+        }
+        c += t[4];
+        t[4] = (uint64_t)c;
+        t[5] = (uint64_t)(c >> 64);
+        uint64_t m = t[0] * ninv;
+        c = ((u128)m * P[0] + t[0]) >> 64;
+        for (int j = 1; j < 4; ++j) {
+          c += (u128)m * P[j] + t[j];
+          t[j - 1] = (uint64_t)c;
+          c >>= 64;
+        }
+        c += t[4];
+        t[3] = (uint64_t)c;
+        t[4] = t[5] + (uint64_t)(c >> 64);
       }
-      bool ge = (t[8] != 0) || (bw == 0);
-      for (int i = 0; i < 8; ++i)
-        r.v[i] = ge ? u[i] : t[i];
+      uint64_t u[4];
+      unsigned char bw = 0;
+      for (int i = 0; i < 4; ++i) {
+        u128 d = (u128)t[i] - P[i] - bw;
+        u[i] = (uint64_t)d;
+        bw = (unsigned char)((d >> 64) & 1);
+      }
+      bool ge = (t[4] != 0) || (bw == 0);
+      for (int i = 0; i < 4; ++i) {
+        uint64_t x = ge ? u[i] : t[i];
+        r.v[2 * i] = (uint32_t)x;
+        r.v[2 * i + 1] = (uint32_t)(x >> 32);
+      }
 #endif
       return r;
     }

@@ -402,12 +402,11 @@ namespace b200 {
   }
 
   // ---------------------------------------------------------------------------------------------- prove
-  static eIcicleError commit_partials(
-    b200_zkey_cache* c, const bn254_scalar_t* witness, uint32_t n_witness, b200_groth16_partials* out, b200_prove_timings* tm)
+  // enqueue everything up to the device-to-host copy of the five partial sums; returns without waiting
+  static eIcicleError commit_enqueue(b200_zkey_cache* c, const bn254_scalar_t* witness, uint32_t n_witness)
   {
-    if (!c || !witness || !out) return ICICLE_INVALID_POINTER;
+    if (!c || !witness) return ICICLE_INVALID_POINTER;
     if (n_witness != c->n_vars) return ICICLE_INVALID_ARGUMENT; // "Invalid witness length" (proof_helper.rs:259-264)
-    std::lock_guard<std::mutex> g(c->mu);
     B200_CUDA(cudaSetDevice(c->device), ICICLE_INVALID_DEVICE);
     const uint32_t N = c->domain_size;
     G1Projective* r_a = (G1Projective*)c->d_results;
@@ -468,6 +467,12 @@ namespace b200 {
     B200_CUDA(
       cudaMemcpyAsync(c->h_results, c->d_results, 4 * 96 + 192, cudaMemcpyDeviceToHost, c->s_copy), ICICLE_COPY_FAILED);
     B200_CUDA(cudaEventRecord(c->ev_prev, c->s_copy), ICICLE_UNKNOWN_FALLBACK);
+    return ICICLE_SUCCESS;
+  }
+
+  static eIcicleError commit_wait(b200_zkey_cache* c, b200_groth16_partials* out, b200_prove_timings* tm)
+  {
+    if (!c || !out) return ICICLE_INVALID_POINTER;
     B200_CUDA(cudaStreamSynchronize(c->s_copy), ICICLE_SYNCHRONIZATION_FAILED);
     B200_CUDA(cudaGetLastError(), ICICLE_UNKNOWN_FALLBACK);
 
@@ -500,6 +505,15 @@ namespace b200 {
     return ICICLE_SUCCESS;
   }
 
+  static eIcicleError commit_partials(
+    b200_zkey_cache* c, const bn254_scalar_t* witness, uint32_t n_witness, b200_groth16_partials* out, b200_prove_timings* tm)
+  {
+    if (!c || !witness || !out) return ICICLE_INVALID_POINTER;
+    std::lock_guard<std::mutex> g(c->mu);
+    B200_TRY(commit_enqueue(c, witness, n_witness));
+    return commit_wait(c, out, tm);
+  }
+
   template <class F>
   static XYZZ<F> load_partial(const void* p)
   {
@@ -508,22 +522,39 @@ namespace b200 {
     return xyzz_from_projective(proj_to_mont(pr));
   }
 
-  // Blinding epilogue (proof_helper.rs:274-295) on the host; ~6 scalar multiplications.
-  static eIcicleError finish(
-    const b200_zkey_cache* c, const b200_groth16_partials* parts, int n_parts, const bn254_scalar_t* r_in,
-    const bn254_scalar_t* s_in, b200_groth16_proof* proof)
+  // Blinding epilogue (proof_helper.rs:274-295) on the host.  The four multiples of delta depend only on (r, s):
+  // they are computed while the GPU is still busy; two scalar multiplications of MSM results remain afterwards.
+  struct BlindTerms {
+    Fr r, s;
+    G1XYZZ r_d1, s_d1, rs_d1;
+    G2XYZZ s_d2;
+  };
+
+  static void compute_blind(const b200_zkey_cache* c, const bn254_scalar_t* r_in, const bn254_scalar_t* s_in, BlindTerms& b)
+  {
+    if (r_in && s_in) {
+      memcpy(&b.r, r_in, 32);
+      memcpy(&b.s, s_in, 32);
+    } else { // ScalarCfg::generate_random(2) (proof_helper.rs:276-278)
+      std::mt19937_64 rng(std::random_device{}());
+      b.r = host_random_fr(rng);
+      b.s = host_random_fr(rng);
+    }
+    G1XYZZ d1 = G1XYZZ::from_affine(c->delta1);
+    G2XYZZ d2 = G2XYZZ::from_affine(c->delta2);
+    Fr rs = Fr::from_mont(Fr::to_mont(b.r) * Fr::to_mont(b.s));
+    b.r_d1 = host_scalar_mul(d1, b.r);
+    b.s_d1 = host_scalar_mul(d1, b.s);
+    b.rs_d1 = host_scalar_mul(d1, rs);
+    b.s_d2 = host_scalar_mul(d2, b.s);
+  }
+
+  static eIcicleError finish_with(
+    const b200_zkey_cache* c, const b200_groth16_partials* parts, int n_parts, const BlindTerms& bt, b200_groth16_proof* proof)
   {
     if (!c || !parts || !proof) return ICICLE_INVALID_POINTER;
     if (n_parts < 1) return ICICLE_INVALID_ARGUMENT;
-    Fr r, s;
-    if (r_in && s_in) {
-      memcpy(&r, r_in, 32);
-      memcpy(&s, s_in, 32);
-    } else { // ScalarCfg::generate_random(2) (proof_helper.rs:276-278)
-      std::mt19937_64 rng(std::random_device{}());
-      r = host_random_fr(rng);
-      s = host_random_fr(rng);
-    }
+    const Fr &r = bt.r, &s = bt.s;
     G1XYZZ A = G1XYZZ::inf(), B1 = G1XYZZ::inf(), C = G1XYZZ::inf(), H = G1XYZZ::inf();
     G2XYZZ B2 = G2XYZZ::inf();
     for (int i = 0; i < n_parts; ++i) { // fold the per-rank partial sums
@@ -533,27 +564,24 @@ namespace b200 {
       H.add(load_partial<Fq>(&parts[i].h));
       B2.add(load_partial<Fq2>(&parts[i].b2));
     }
-    G1XYZZ d1 = G1XYZZ::from_affine(c->delta1);
-    G2XYZZ d2 = G2XYZZ::from_affine(c->delta2);
     // pi_a = A + alpha1 + r*delta1
     G1XYZZ pi_a = A;
     pi_a.madd(c->alpha1);
-    pi_a.add(host_scalar_mul(d1, r));
+    pi_a.add(bt.r_d1);
     // pi_b = B2 + beta2 + s*delta2
     G2XYZZ pi_b = B2;
     pi_b.madd(c->beta2);
-    pi_b.add(host_scalar_mul(d2, s));
+    pi_b.add(bt.s_d2);
     // pi_b1 = B1 + beta1 + s*delta1
     G1XYZZ pi_b1 = B1;
     pi_b1.madd(c->beta1);
-    pi_b1.add(host_scalar_mul(d1, s));
+    pi_b1.add(bt.s_d1);
     // pi_c = C + H + s*pi_a + r*pi_b1 - (r*s)*delta1
-    Fr rs = Fr::from_mont(Fr::to_mont(r) * Fr::to_mont(s));
     G1XYZZ pi_c = C;
     pi_c.add(H);
     pi_c.add(host_scalar_mul(pi_a, s));
     pi_c.add(host_scalar_mul(pi_b1, r));
-    pi_c.add(host_scalar_mul(d1, rs).neg());
+    pi_c.add(bt.rs_d1.neg());
 
     G1Affine a = affine_from_mont(pi_a.to_affine());
     G2Affine b = affine_from_mont(pi_b.to_affine());
@@ -704,7 +732,10 @@ eIcicleError b200_groth16_finish(
   const b200_zkey_cache* cache, const b200_groth16_partials* parts, int n_parts, const bn254_scalar_t* r,
   const bn254_scalar_t* s, b200_groth16_proof* proof)
 {
-  return finish(cache, parts, n_parts, r, s, proof);
+  if (!cache) return ICICLE_INVALID_POINTER;
+  BlindTerms bt;
+  compute_blind(cache, r, s, bt);
+  return finish_with(cache, parts, n_parts, bt, proof);
 }
 
 eIcicleError b200_groth16_prove(
@@ -714,8 +745,12 @@ eIcicleError b200_groth16_prove(
   if (!cache || !proof) return ICICLE_INVALID_POINTER;
   if (cache->world != 1) return ICICLE_INVALID_ARGUMENT; // sharded caches go through commit_partials + finish
   b200_groth16_partials parts;
-  B200_TRY(commit_partials(cache, witness, n_witness, &parts, tm));
-  return finish(cache, &parts, 1, r, s, proof);
+  std::lock_guard<std::mutex> g(cache->mu);
+  B200_TRY(commit_enqueue(cache, witness, n_witness));
+  BlindTerms bt;
+  compute_blind(cache, r, s, bt); // host work overlapped with the GPU
+  B200_TRY(commit_wait(cache, &parts, tm));
+  return finish_with(cache, &parts, 1, bt, proof);
 }
 
 eIcicleError b200_groth16_prove_files(

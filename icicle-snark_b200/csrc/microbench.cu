@@ -110,34 +110,112 @@ namespace b200 {
   struct F29 {
     uint32_t v[9];
   };
+  // 9x29-bit Montgomery product, R = 2^261, operand scanning with a sliding window of nine 64-bit columns.
+  // Every partial product is a plain IMAD.WIDE (64-bit accumulate, no carry in/out): limbs < 2^30 keep a column
+  // below 2^64 over its 18 terms.  Output limbs < 2^29 (top limb slightly more), value < 2p for inputs < 4p.
+  template <bool CONST_IN_REGS>
   __device__ __forceinline__ F29 mul29(const F29& a, const F29& b)
   {
     constexpr uint32_t MASK = (1u << 29) - 1, PINV = 0x4866389u;
-    constexpr uint32_t PL[9] = {0x187cfd47, 0x10460b6, 0x1c72a34f, 0x2d522d0, 0x1585d978, 0x2db40c0, 0xa6e141, 0xe5c2634, 0x30644e};
-    uint64_t c[18];
+    constexpr uint32_t PLc[9] = {0x187cfd47, 0x10460b6, 0x1c72a34f, 0x2d522d0, 0x1585d978, 0x2db40c0, 0xa6e141, 0xe5c2634, 0x30644e};
+    uint32_t PL[9];
 #pragma unroll
-    for (int k = 0; k < 18; ++k)
-      c[k] = 0;
+    for (int j = 0; j < 9; ++j) {
+      PL[j] = PLc[j];
+      if (CONST_IN_REGS) asm volatile("mov.u32 %0, %1;" : "=r"(PL[j]) : "r"(PLc[j])); // keep the modulus in registers
+    }
+    uint64_t c[10];
+#pragma unroll
+    for (int j = 0; j < 9; ++j)
+      asm("mul.wide.u32 %0, %1, %2;" : "=l"(c[j]) : "r"(a.v[j]), "r"(b.v[0]));
 #pragma unroll
     for (int i = 0; i < 9; ++i) {
+      if (i > 0) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(c[j]) : "r"(a.v[j]), "r"(b.v[i]));
+        asm("mul.wide.u32 %0, %1, %2;" : "=l"(c[8]) : "r"(a.v[8]), "r"(b.v[i]));
+      }
+      uint32_t m = ((uint32_t)c[0] * PINV) & MASK;
 #pragma unroll
       for (int j = 0; j < 9; ++j)
-        c[i + j] += (uint64_t)a.v[j] * b.v[i];
-      uint32_t m = ((uint32_t)c[i] * PINV) & MASK;
+        asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(c[j]) : "r"(m), "r"(PL[j]));
+      uint64_t carry = c[0] >> 29;
 #pragma unroll
-      for (int j = 0; j < 9; ++j)
-        c[i + j] += (uint64_t)m * PL[j];
-      c[i + 1] += c[i] >> 29;
+      for (int j = 0; j < 8; ++j)
+        c[j] = c[j + 1];
+      c[0] += carry;
     }
     F29 r;
     uint64_t carry = 0;
 #pragma unroll
     for (int k = 0; k < 9; ++k) {
-      uint64_t v = c[9 + k] + carry;
+      uint64_t v = c[k] + carry;
       r.v[k] = k < 8 ? (uint32_t)v & MASK : (uint32_t)v;
       carry = v >> 29;
     }
     return r;
+  }
+
+  // 8x32 (value < 2^256) <-> 9x29
+  __device__ __forceinline__ F29 to29(const Fq& x)
+  {
+    F29 r;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+      int bit = 29 * k, w = bit >> 5, sh = bit & 31;
+      uint64_t two = x.v[w];
+      if (w + 1 < 8) two |= (uint64_t)x.v[w + 1] << 32;
+      r.v[k] = (uint32_t)(two >> sh) & ((1u << 29) - 1);
+    }
+    return r;
+  }
+  __device__ __forceinline__ Fq from29(const F29& x) // value must be < 2^256
+  {
+    Fq r = Fq::zero();
+    uint64_t acc = 0;
+    int filled = 0, w = 0;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+      acc |= (uint64_t)x.v[k] << filled;
+      filled += 29;
+      if (filled >= 32 && w < 8) {
+        r.v[w++] = (uint32_t)acc;
+        acc >>= 32;
+        filled -= 32;
+      }
+    }
+    if (w < 8) r.v[w] = (uint32_t)acc;
+    return r;
+  }
+
+  // self-check: 32 * mul29(a,b) == CIOS(a,b) mod q  (R differs by 2^5). Returns mismatches in *bad.
+  __global__ void mul29_check_kernel(uint32_t seed, int* bad)
+  {
+    uint32_t st = seed + blockIdx.x * 977u + threadIdx.x * 131u;
+    Fq a, b;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      st = st * 1664525u + 1013904223u;
+      a.v[i] = st;
+      st = st * 1664525u + 1013904223u;
+      b.v[i] = st;
+    }
+    a.v[7] &= 0x1fffffffu; // < 2^253 < q
+    b.v[7] &= 0x1fffffffu;
+    Fq want = a * b;
+    F29 y = mul29<true>(to29(a), to29(b));
+    F29 y2 = mul29<false>(to29(a), to29(b));
+    Fq got = from29(y), got2 = from29(y2);
+    // canonical reduce (result < 2q), then x32
+    Fq zero = Fq::zero();
+    got = got + zero;
+    got2 = got2 + zero;
+    for (int k = 0; k < 5; ++k) {
+      got = got.dbl();
+      got2 = got2.dbl();
+    }
+    if (got != want || got2 != want) atomicAdd(bad, 1);
   }
 
   template <int MODE>
@@ -174,7 +252,7 @@ namespace b200 {
       for (int it = 0; it < iters; ++it) {
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-          x[k] = mul29(x[k], y);
+          x[k] = mul29<MODE == 8>(x[k], y);
       }
       uint32_t s = 0;
 #pragma unroll
@@ -213,8 +291,10 @@ extern "C" double b200_pipe_peak(int mode)
       const int it2 = 512, bl2 = sm_count() * 8;
       if (mode == 6)
         fieldmul_kernel<6><<<bl2, 128>>>((uint32_t*)d, it2, rep);
-      else
+      else if (mode == 7)
         fieldmul_kernel<7><<<bl2, 128>>>((uint32_t*)d, it2, rep);
+      else
+        fieldmul_kernel<8><<<bl2, 128>>>((uint32_t*)d, it2, rep);
       cudaEventRecord(e1, 0);
       if (cudaEventSynchronize(e1) != cudaSuccess) break;
       float ms2 = 0;
@@ -243,6 +323,20 @@ extern "C" double b200_pipe_peak(int mode)
   cudaEventDestroy(e1);
   cudaFree(d);
   return best;
+}
+
+// number of mismatching products between the 9x29 candidate and the production multiplier (0 = agree)
+extern "C" int b200_mul29_selfcheck(void)
+{
+  if (ensure_device() != ICICLE_SUCCESS) return -1;
+  int* d = nullptr;
+  if (cudaMalloc((void**)&d, 4) != cudaSuccess) return -1;
+  cudaMemset(d, 0, 4);
+  mul29_check_kernel<<<64, 128>>>(12345u, d);
+  int h = -1;
+  cudaMemcpy(&h, d, 4, cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  return h;
 }
 
 // the roofline denominator used by bench.py: wide (32x32+64) multiply-adds per second in carry chains

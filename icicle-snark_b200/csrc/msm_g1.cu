@@ -24,7 +24,8 @@ namespace b200 {
       // so wider windows (fewer adds per scalar) pay
       if (c < 2) c = 2;
       int w0 = (bitsize + 2 + c - 1) / c;
-      if (factor >= w0 && w0 > 1 && lg >= 12) c = lg - 1 < 21 ? lg - 1 : 21;
+      // (small inputs: more, shorter buckets so that one thread per bucket still fills the machine)
+      if (factor >= w0 && w0 > 1 && lg >= 12) c = lg + 1 < 21 ? lg + 1 : 21;
       // a top window holding only 1..4 bits of the scalar funnels n/2^bits entries into each of a few
       // buckets; step down until the top window is either empty or reasonably wide
       while (c > 2) {
