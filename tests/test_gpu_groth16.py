@@ -123,3 +123,39 @@ def test_msm_known_dlog_at_scale(gpu, rng):
     dot = sum(a * b for a, b in zip(sv, kv)) % R
     want = gpu.mul_scalar(gpu.generator(), ints_to_array([dot])[0])
     assert np.array_equal(gpu.to_affine(got), gpu.to_affine(want))
+
+
+def test_aadhaar_shaped_substitute_matches_oracle(gpu, ref):
+    """configs[3] substitute (anon_aadhaar itself needs circom/circomlib/snarkjs): random satisfiable R1CS with
+    multi-entry rows (collisions in the A/B accumulation), 9 public inputs and a ~90 % 0/1 witness (giant buckets:
+    exercises the item split + fold path of the MSM inside the prover)."""
+    zkey, wtns, vk = synth.make_random_circuit(gpu, 20000, n_inputs=300, n_public=9)
+    w = wtns_words(wtns)
+    vals = [int.from_bytes(x.tobytes(), "little") for x in w]
+    assert sum(v in (0, 1) for v in vals) / len(vals) > 0.8
+    proof_ref, public = G.prove(ref, pkg.bindings, zkey, wtns, FIXED_R, FIXED_S)
+    assert len(public) == 9 and G.verify(ref, proof_ref, public, vk)
+    for precompute in (1, 16):
+        cache = pkg.ZKeyCache(gpu, zkey, precompute=precompute)
+        try:
+            p, _ = cache.prove(w, FIXED_R, FIXED_S)
+            assert pkg.proof_json(p) == G.proof_json(proof_ref)
+        finally:
+            cache.close()
+
+
+def test_full_size_proof_verifies_under_reference_pairing(gpu, ref):
+    """Size-independent property at a benchmark size (800k constraints): the GPU proof with random blinding verifies
+    under the reference's own pairing; a second proof of the same witness differs (fresh r, s) and verifies too."""
+    zkey, wtns, vk = synth.make_complex_circuit(gpu, 800_000)
+    cache = pkg.ZKeyCache(gpu, zkey, precompute=16)
+    try:
+        w = wtns_words(wtns)
+        public = [int.from_bytes(w[1].tobytes(), "little")]
+        p1, tm = cache.prove(w)
+        p2, _ = cache.prove(w)
+        assert pkg.proof_json(p1) != pkg.proof_json(p2)
+        assert G.verify(ref, pkg.proof_to_dict(p1), public, vk) and G.verify(ref, pkg.proof_to_dict(p2), public, vk)
+        assert not G.verify(ref, pkg.proof_to_dict(p1), [public[0] ^ 1], vk)
+    finally:
+        cache.close()

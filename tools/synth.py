@@ -171,3 +171,91 @@ def make_complex_circuit(backend, n, seed=b"icicle-snark-b200", a=3, log=None):
     vk = dict(alpha1=std1[0], beta2=std2[0], gamma2=std2[1], delta2=std2[2],
               ic=backend.convert_montgomery(pIC, False, kind="affine"), n_public=n_public)
     return zkey, wtns, vk
+
+
+def make_random_circuit(backend, n_constraints, n_inputs=64, n_public=9, max_terms=6, zero_one_fraction=0.9, seed=b"aadhaar-shaped",
+                        rng_seed=7):
+    """"aadhaar-shaped" SUBSTITUTE for benchmark/anon_aadhaar (which needs circom + circomlib + snarkjs, unavailable
+    offline): a satisfiable random R1CS with multi-entry rows and a 0/1-heavy witness.
+    Constraint k multiplies two random sparse linear combinations of earlier signals (1..max_terms terms, small
+    coefficients) and defines a NEW signal as the product, so every constraint is satisfied by construction:
+        (sum a_t w_{i_t}) * (sum b_t w_{j_t}) = w_{new}.
+    About `zero_one_fraction` of the constraints are booleanity-style (b * b = b over a 0/1 input signal... realised
+    as product of two 0/1 signals), which keeps ~90 % of the witness in {0,1} like a SHA/RSA bit-decomposed circuit.
+    n_public signals (the first inputs) are public, as anon_aadhaar has 9.  Returns (zkey, wtns, vk)."""
+    import random
+    rnd = random.Random(rng_seed)
+    n_vars = 1 + n_inputs + n_constraints
+    power = (n_constraints + n_public + 1 - 1).bit_length()
+    N = 1 << power
+    tw = toxic(seed)
+    tau, alpha, beta, gamma, delta = (tw[k] for k in ("tau", "alpha", "beta", "gamma", "delta"))
+    dinv, ginv = pow(delta, -1, R), pow(gamma, -1, R)
+    # witness + sparse rows
+    w = [1] + [rnd.randrange(2) if rnd.random() < zero_one_fraction else rnd.randrange(R) for _ in range(n_inputs)]
+    A_rows, B_rows, C_sig = [], [], []
+    bits = [i for i in range(1, n_inputs + 1) if w[i] in (0, 1)] or [1]
+    for k in range(n_constraints):
+        new = 1 + n_inputs + k
+        if rnd.random() < zero_one_fraction:
+            i, j = rnd.choice(bits), rnd.choice(bits)
+            ra, rb = [(i, 1)], [(j, 1)]
+        else:
+            hi = new
+            ra = [(rnd.randrange(hi), rnd.randrange(1, 1 << 16)) for _ in range(rnd.randint(1, max_terms))]
+            rb = [(rnd.randrange(hi), rnd.randrange(1, 1 << 16)) for _ in range(rnd.randint(1, max_terms))]
+        va = sum(c * w[s] for s, c in ra) % R
+        vb = sum(c * w[s] for s, c in rb) % R
+        w.append(va * vb % R)
+        if w[-1] in (0, 1):
+            bits.append(new)
+        A_rows.append(ra)
+        B_rows.append(rb)
+        C_sig.append(new)
+    assert len(w) == n_vars
+
+    backend.ntt_release_domain()
+    backend.ntt_init_domain(backend.get_root_of_unity(2 * N))
+    try:
+        L = words_to_ints(lagrange_at_tau(backend, tau, power))
+        L2 = lagrange_at_tau(backend, tau, power + 1)
+    finally:
+        backend.ntt_release_domain()
+    u, v, wv = [0] * n_vars, [0] * n_vars, [0] * n_vars
+    recs = []
+    for k in range(n_constraints):
+        for s, c in A_rows[k]:
+            u[s] = (u[s] + c * L[k]) % R
+            recs.append((0, k, s, c))
+        for s, c in B_rows[k]:
+            v[s] = (v[s] + c * L[k]) % R
+            recs.append((1, k, s, c))
+        wv[C_sig[k]] = (wv[C_sig[k]] + L[k]) % R
+    for i in range(n_public + 1):  # snarkjs public-input rows
+        u[i] = (u[i] + L[n_constraints + i]) % R
+        recs.append((0, n_constraints + i, i, 1))
+    comb = [(beta * u[s] + alpha * v[s] + wv[s]) % R for s in range(n_vars)]
+    pA = fixed_base(backend, ints_to_words(u))
+    pB1 = fixed_base(backend, ints_to_words(v))
+    pB2 = fixed_base(backend, ints_to_words(v), g2=True)
+    pC = fixed_base(backend, ints_to_words([x * dinv % R for x in comb[n_public + 1:]]))
+    pIC = fixed_base(backend, ints_to_words([x * ginv % R for x in comb[:n_public + 1]]))
+    pH = fixed_base(backend, backend.scalar_mul_vec(word(dinv), np.ascontiguousarray(L2[1::2])))
+    vk1 = fixed_base(backend, ints_to_words([alpha, beta, delta]))
+    vk2 = fixed_base(backend, ints_to_words([beta, gamma, delta]), g2=True)
+    r2 = MONT_R * MONT_R % R
+    sec4 = struct.pack("<I", len(recs)) + b"".join(
+        struct.pack("<III", m, row, s) + (c * r2 % R).to_bytes(32, "little") for m, row, s, c in recs)
+    header = (struct.pack("<I", 32) + Q.to_bytes(32, "little") + struct.pack("<I", 32) + R.to_bytes(32, "little") +
+              struct.pack("<III", n_vars, n_public, N) + vk1[0].tobytes() + vk1[1].tobytes() + vk2[0].tobytes() +
+              vk2[1].tobytes() + vk1[2].tobytes() + vk2[2].tobytes())
+    sections = [(1, struct.pack("<I", 1)), (2, header), (3, pIC.tobytes()), (4, sec4), (5, pA.tobytes()), (6, pB1.tobytes()),
+                (7, pB2.tobytes()), (8, pC.tobytes()), (9, pH.tobytes())]
+    zkey = b"zkey" + struct.pack("<II", 1, len(sections)) + b"".join(_section(i, p) for i, p in sections)
+    wt_hdr = struct.pack("<I", 32) + R.to_bytes(32, "little") + struct.pack("<I", n_vars)
+    wtns = (b"wtns" + struct.pack("<II", 2, 2) + _section(1, wt_hdr) + _section(2, b"".join(x.to_bytes(32, "little") for x in w)))
+    std1 = backend.convert_montgomery(vk1, False, kind="affine")
+    std2 = backend.convert_montgomery(vk2, False, kind="g2_affine")
+    vk = dict(alpha1=std1[0], beta2=std2[0], gamma2=std2[1], delta2=std2[2],
+              ic=backend.convert_montgomery(pIC, False, kind="affine"), n_public=n_public)
+    return zkey, wtns, vk
