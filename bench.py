@@ -266,7 +266,10 @@ def main():
     alg_mac = n_msm * windows * 10 * 136            # 10 field mults per mixed add, 136 32x32 multiply-adds each
     roofline = {
         "kernel": "msm_accumulate_kernel<Fq>", "bound": "hbm", "achieved": alg_bytes / (acc * 1e-3) / 1e9, "peak": hbm_peak,
-        "unit": "GB/s", "frac": alg_bytes / (acc * 1e-3) / 1e9 / hbm_peak, "traffic": None, "peak_source": peak_src,
+        "unit": "GB/s", "frac": alg_bytes / (acc * 1e-3) / 1e9 / hbm_peak,
+        # dram__bytes_read.sum + dram__bytes_write.sum of this very launch shape from the committed ncu capture
+        # (profiles/r01_ncu_msm_accumulate_g1_3200k.md); other sizes were not captured
+        "traffic": 4.426e9 if n_msm == 3200002 else None, "algorithmic_bytes": alg_bytes, "peak_source": peak_src,
         "launch_ms": acc, "units_per_launch": f"{n_msm} scalars x {windows} windows (c={c_bits})",
         "int_pipe": {"achieved_tmac_s": alg_mac / (acc * 1e-3) / 1e12, "peak_tmac_s": imad_peak / 1e12,
                      "frac": alg_mac / (acc * 1e-3) / imad_peak,

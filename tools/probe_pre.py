@@ -5,7 +5,7 @@ import __graft_entry__ as g
 pkg = g.load_package(); B = pkg.bindings; lib = pkg.lib(); lib.set_device("CUDA", 0)
 from tools import synth
 lg = int(sys.argv[1]); f = int(sys.argv[2]); c = int(sys.argv[3]); g2 = len(sys.argv) > 4
-n = 1 << lg
+n = lg if lg > 64 else 1 << lg
 rng = np.random.default_rng(5)
 sc = rng.integers(0, 1 << 32, size=(n, 8), dtype=np.uint64).astype(np.uint32); sc[:, 7] &= 0x0FFFFFFF
 k = rng.integers(0, 1 << 32, size=(n, 8), dtype=np.uint64).astype(np.uint32); k[:, 7] &= 0x0FFFFFFF
