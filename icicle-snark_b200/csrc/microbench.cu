@@ -264,6 +264,38 @@ namespace b200 {
     }
   }
 
+  // mode 9: "carry-save" wide multiply-add: IMAD.WIDE with carry-OUT only (no carry-in) + a counter bumped by the
+  // carry on the ALU pipe - the building block of a multiplier without IMAD.WIDE.X chains
+  __global__ void __launch_bounds__(256) carrysave_kernel(uint64_t* out, int iters, uint32_t seed)
+  {
+    uint32_t b = (threadIdx.x * 2654435761u + seed) | 1u, c = blockIdx.x + 12345u;
+    uint64_t acc[8];
+    uint32_t cnt[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      acc[k] = threadIdx.x + k;
+      cnt[k] = 0;
+    }
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        asm volatile(
+          "{ .reg .u32 l, h;\n\t"
+          "mov.b64 {l, h}, %0;\n\t"
+          "mad.lo.cc.u32 l, %2, %3, l;\n\t"
+          "madc.hi.cc.u32 h, %2, %3, h;\n\t"
+          "addc.u32 %1, %1, 0;\n\t"
+          "mov.b64 %0, {l, h}; }"
+          : "+l"(acc[k]), "+r"(cnt[k])
+          : "r"(b), "r"(c));
+    }
+    uint64_t sink = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+      sink ^= acc[k] + cnt[k];
+    if (sink == 0x123456789abcdefull) out[0] = sink;
+  }
+
   template <int MODE>
   static void launch_pipe(uint64_t* d, int iters, int blocks, int rep)
   {
@@ -287,6 +319,16 @@ extern "C" double b200_pipe_peak(int mode)
   double best = -1.0;
   for (int rep = 0; rep < 5; ++rep) {
     cudaEventRecord(e0, 0);
+    if (mode == 9) {
+      carrysave_kernel<<<blocks, 256>>>(d, iters, rep);
+      cudaEventRecord(e1, 0);
+      if (cudaEventSynchronize(e1) != cudaSuccess) break;
+      float ms9 = 0;
+      cudaEventElapsedTime(&ms9, e0, e1);
+      double r9 = (double)blocks * 256 * iters * 8 / (ms9 * 1e-3);
+      if (r9 > best) best = r9;
+      continue;
+    }
     if (mode >= 6) {
       const int it2 = 512, bl2 = sm_count() * 8;
       if (mode == 6)

@@ -38,6 +38,40 @@ namespace b200 {
 
   MsmPlan make_msm_plan(int n, int c_req, int bitsize, int factor, bool g2);
 
+  struct MsmDev { // plan fields the kernels need, passed by value
+    int n, c, windows, factor, sets, bpw, nbuckets, item_cap;
+    uint32_t h[9];
+  };
+  MsmDev msm_dev_plan(const MsmPlan& plan);
+
+  struct MsmItem {
+    uint32_t begin;  // first entry
+    uint32_t len;    // 1..T
+    uint32_t bucket; // bucket key
+    uint32_t dst;    // index into `buckets` (single-item bucket) or 0x80000000|index into `partials`
+  };
+
+  // Result of the group-independent sort phase (msm_sort.cu): bucket-sorted point references + work items.
+  struct MsmSorted {
+    uint8_t* base = nullptr;       // scratch block (stream-ordered allocation), freed by msm_sorted_free
+    uint32_t* entries = nullptr;   // (point index | sign << 31), bucket-sorted
+    uint32_t* offsets = nullptr;   // nbuckets + 1 exclusive offsets into entries
+    uint32_t* item_off = nullptr;  // nbuckets + 1; item_off[nbuckets] = number of work items (device side)
+    uint32_t* multi = nullptr;     // keys of buckets cut into several items
+    uint32_t* multi_count = nullptr;
+    MsmItem* sorted = nullptr;     // work items, longest first
+    size_t max_items = 0;
+  };
+  eIcicleError msm_sort_enqueue(const MsmPlan& plan, const Fr* scalars, bool scalars_mont, MsmSorted* out, cudaStream_t st);
+  void msm_sorted_free(MsmSorted* s, cudaStream_t st);
+
+  // Accumulate + reduce `nsel` (<= 4) MSMs that share `sorted` (same scalars, same plan) over different base-point
+  // arrays; out_std[k] receives MSM k in the reference's boundary layout.
+  template <class F>
+  eIcicleError msm_reduce_enqueue(
+    const MsmPlan& plan, const MsmSorted& sorted, const Affine<F>* const* bases_mont, int nsel, Projective<F>* out_std,
+    cudaStream_t st);
+
   // Enqueue one MSM on `st`.  All pointers are DEVICE pointers; `bases_mont` holds n*factor affine
   // points in Montgomery form ([i*f + j] = 2^(shift*j) P_i); `out_std` receives the result in the
   // reference's boundary layout (homogeneous projective, standard form).

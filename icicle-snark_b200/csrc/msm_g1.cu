@@ -55,6 +55,7 @@ namespace b200 {
   }
 
   template eIcicleError msm_enqueue<Fq>(const MsmPlan&, const Fr*, bool, const Affine<Fq>*, Projective<Fq>*, cudaStream_t);
+  template eIcicleError msm_reduce_enqueue<Fq>(const MsmPlan&, const MsmSorted&, const Affine<Fq>* const*, int, Projective<Fq>*, cudaStream_t);
   template eIcicleError precompute_enqueue<Fq>(const Affine<Fq>*, bool, int, int, int, Affine<Fq>*, bool, cudaStream_t);
 
 } // namespace b200

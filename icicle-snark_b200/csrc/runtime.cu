@@ -37,6 +37,12 @@ namespace b200 {
         B200_CUDA(cudaDeviceGetDefaultMemPool(&pool, dev), ICICLE_INVALID_DEVICE);
         uint64_t keep = UINT64_MAX;
         B200_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep), ICICLE_INVALID_DEVICE);
+        // Never let the pool hand stream B a block whose free is still pending on stream A: that inserts a
+        // hidden B-after-A dependency and serialises the five concurrent MSM streams of a proof (their scratch
+        // blocks are the same size). Reuse only memory whose free has already completed; the pool simply grows
+        // to the concurrent peak (a few GB of 180).
+        int off = 0;
+        B200_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolReuseAllowInternalDependencies, &off), ICICLE_INVALID_DEVICE);
         int n = 0;
         B200_CUDA(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev), ICICLE_INVALID_DEVICE);
         g_sm_count[dev] = n;
