@@ -196,24 +196,29 @@ namespace b200 {
     delete c;
   }
 
-  // upload the [lo,hi) slice of a base-point section; with precompute > 1 expand it into the
-  // [i*f + j] = 2^(shift*j) P_i table the MSM consumes (cuda_msm.cuh:29-43 layout)
+  // Upload the [lo,hi) slice of the logical array  zeros(prefix) ++ section  (prefix points at infinity in front let
+  // the C section, which starts at signal n_public+1, share the witness indexing of A/B1/B2); with precompute > 1
+  // expand it into the [i*f + j] = 2^(shift*j) P_i table the MSM consumes (cuda_msm.cuh:29-43 layout)
   template <class F>
   static eIcicleError upload_points(
-    b200_zkey_cache* c, const Section& sec, uint32_t lo, uint32_t hi, const MsmPlan& plan, Affine<F>** out, cudaStream_t st)
+    b200_zkey_cache* c, const Section& sec, uint32_t prefix, uint32_t lo, uint32_t hi, const MsmPlan& plan, Affine<F>** out,
+    cudaStream_t st)
   {
     const size_t n = hi - lo;
     const int f = plan.factor;
     B200_CUDA(dev_alloc(out, n * f, c), ICICLE_ALLOCATION_FAILED);
     if (n == 0) return ICICLE_SUCCESS;
-    const uint8_t* src = sec.p + (size_t)lo * sizeof(Affine<F>);
-    if (f == 1) {
-      B200_CUDA(cudaMemcpyAsync(*out, src, n * sizeof(Affine<F>), cudaMemcpyHostToDevice, st), ICICLE_COPY_FAILED);
-      return ICICLE_SUCCESS;
+    Affine<F>* tmp = *out;
+    if (f > 1) B200_CUDA(cudaMallocAsync((void**)&tmp, n * sizeof(Affine<F>), st), ICICLE_ALLOCATION_FAILED);
+    const size_t nz = lo < prefix ? std::min<size_t>(prefix - lo, n) : 0; // leading points at infinity in this slice
+    if (nz) B200_CUDA(cudaMemsetAsync(tmp, 0, nz * sizeof(Affine<F>), st), ICICLE_COPY_FAILED);
+    if (n > nz) {
+      const size_t first = (lo + nz) - prefix; // index into the section
+      B200_CUDA(
+        cudaMemcpyAsync(tmp + nz, sec.p + first * sizeof(Affine<F>), (n - nz) * sizeof(Affine<F>), cudaMemcpyHostToDevice, st),
+        ICICLE_COPY_FAILED);
     }
-    Affine<F>* tmp = nullptr;
-    B200_CUDA(cudaMallocAsync((void**)&tmp, n * sizeof(Affine<F>), st), ICICLE_ALLOCATION_FAILED);
-    B200_CUDA(cudaMemcpyAsync(tmp, src, n * sizeof(Affine<F>), cudaMemcpyHostToDevice, st), ICICLE_COPY_FAILED);
+    if (f == 1) return ICICLE_SUCCESS;
     eIcicleError e = precompute_enqueue<F>(tmp, true, (int)n, f, plan.c * plan.sets, *out, true, st);
     cudaFreeAsync(tmp, st);
     return e;
@@ -311,21 +316,25 @@ namespace b200 {
     cudaStream_t st = c->s_copy;
 
     // ---- base points: this rank's contiguous shard of every section
+    // A, B1, B2 and C (padded in front with n_public+1 points at infinity) are all indexed by signal, so the four
+    // witness MSMs share one shard range, one plan and one sort
     shard(c->n_vars, rank, world, &c->a_lo, &c->a_hi);
-    shard(n_c, rank, world, &c->c_lo, &c->c_hi);
+    c->c_lo = c->a_lo;
+    c->c_hi = c->a_hi;
     shard(N, rank, world, &c->h_lo, &c->h_hi);
     auto plan_for = [&](uint32_t n, bool g2) {
       return make_msm_plan(n ? (int)n : 1, 0, 254, c->precompute, g2);
     };
     c->planA = plan_for(c->a_hi - c->a_lo, false);
-    c->planC = plan_for(c->c_hi - c->c_lo, false);
+    c->planC = c->planA;
+    c->planB2 = c->planA; // same digits/windows as the G1 MSMs: B2 reuses their sort
     c->planH = plan_for(c->h_hi - c->h_lo, false);
-    c->planB2 = plan_for(c->a_hi - c->a_lo, true);
-    if ((err = upload_points<Fq>(c, sec[5], c->a_lo, c->a_hi, c->planA, &c->pA, st)) != ICICLE_SUCCESS) return fail(err);
-    if ((err = upload_points<Fq>(c, sec[6], c->a_lo, c->a_hi, c->planA, &c->pB1, st)) != ICICLE_SUCCESS) return fail(err);
-    if ((err = upload_points<Fq2>(c, sec[7], c->a_lo, c->a_hi, c->planB2, &c->pB2, st)) != ICICLE_SUCCESS) return fail(err);
-    if ((err = upload_points<Fq>(c, sec[8], c->c_lo, c->c_hi, c->planC, &c->pC, st)) != ICICLE_SUCCESS) return fail(err);
-    if ((err = upload_points<Fq>(c, sec[9], c->h_lo, c->h_hi, c->planH, &c->pH, st)) != ICICLE_SUCCESS) return fail(err);
+    if ((err = upload_points<Fq>(c, sec[5], 0, c->a_lo, c->a_hi, c->planA, &c->pA, st)) != ICICLE_SUCCESS) return fail(err);
+    if ((err = upload_points<Fq>(c, sec[6], 0, c->a_lo, c->a_hi, c->planA, &c->pB1, st)) != ICICLE_SUCCESS) return fail(err);
+    if ((err = upload_points<Fq2>(c, sec[7], 0, c->a_lo, c->a_hi, c->planB2, &c->pB2, st)) != ICICLE_SUCCESS) return fail(err);
+    if ((err = upload_points<Fq>(c, sec[8], c->n_public + 1, c->c_lo, c->c_hi, c->planC, &c->pC, st)) != ICICLE_SUCCESS)
+      return fail(err);
+    if ((err = upload_points<Fq>(c, sec[9], 0, c->h_lo, c->h_hi, c->planH, &c->pH, st)) != ICICLE_SUCCESS) return fail(err);
 
     // ---- coefficients -> CSR (record layout: cache.rs:126-166)
     const Section& cs = sec[4];
@@ -442,24 +451,26 @@ namespace b200 {
     }
     cudaEventRecord(c->ev_q, c->s_q);
 
-    // witness-only MSMs: A, B1, C on s_g1; B2 on s_g2 (proof_helper.rs:198-206)
+    // witness-only MSMs (proof_helper.rs:198-206): A, B1, C and B2 take the same scalars over signal-indexed point
+    // tables, so ONE digit decomposition + counting sort feeds one G1 accumulate/reduce over three tables (s_g1) and
+    // one G2 accumulate/reduce (s_g2)
     const Fr* w = c->d_witness;
     if (c->a_hi > c->a_lo) {
-      if ((err = msm_enqueue<Fq>(c->planA, w + c->a_lo, false, c->pA, r_a, c->s_g1)) != ICICLE_SUCCESS) return err;
-      if ((err = msm_enqueue<Fq>(c->planA, w + c->a_lo, false, c->pB1, r_b1, c->s_b1)) != ICICLE_SUCCESS) return err;
-      if ((err = msm_enqueue<Fq2>(c->planB2, w + c->a_lo, false, c->pB2, r_b2, c->s_g2)) != ICICLE_SUCCESS) return err;
+      MsmSorted sorted;
+      if ((err = msm_sort_enqueue(c->planA, w + c->a_lo, false, &sorted, c->s_g1)) != ICICLE_SUCCESS) return err;
+      cudaEventRecord(c->ev_b1, c->s_g1); // sort done
+      cudaStreamWaitEvent(c->s_g2, c->ev_b1, 0);
+      const G1Affine* g1_tables[3] = {c->pA, c->pB1, c->pC};
+      const G2Affine* g2_tables[1] = {c->pB2};
+      if ((err = msm_reduce_enqueue<Fq>(c->planA, sorted, g1_tables, 3, r_a, c->s_g1)) != ICICLE_SUCCESS) return err;
+      if ((err = msm_reduce_enqueue<Fq2>(c->planB2, sorted, g2_tables, 1, r_b2, c->s_g2)) != ICICLE_SUCCESS) return err;
+      cudaEventRecord(c->ev_g2, c->s_g2);
+      cudaStreamWaitEvent(c->s_g1, c->ev_g2, 0); // the sort's scratch is released after both consumers
+      msm_sorted_free(&sorted, c->s_g1);
+    } else {
+      cudaEventRecord(c->ev_g2, c->s_g2);
     }
-    if (c->c_hi > c->c_lo) {
-      if ((err = msm_enqueue<Fq>(c->planC, w + c->n_public + 1 + c->c_lo, false, c->pC, r_c, c->s_c)) != ICICLE_SUCCESS)
-        return err;
-    }
-    // every MSM has its own stream: their latency-bound tails (bucket reduction) overlap other MSMs' accumulation
-    cudaEventRecord(c->ev_b1, c->s_b1);
-    cudaEventRecord(c->ev_c, c->s_c);
-    cudaStreamWaitEvent(c->s_g1, c->ev_b1, 0);
-    cudaStreamWaitEvent(c->s_g1, c->ev_c, 0);
     cudaEventRecord(c->ev_g1, c->s_g1);
-    cudaEventRecord(c->ev_g2, c->s_g2);
 
     // join on s_copy, one D2H of the five partial sums
     for (cudaEvent_t e : {c->ev_q, c->ev_g1, c->ev_g2})
@@ -483,9 +494,9 @@ namespace b200 {
     if (c->a_hi == c->a_lo) {
       memcpy(&out->a, &id1, 96);
       memcpy(&out->b1, &id1, 96);
+      memcpy(&out->c, &id1, 96);
       memcpy(&out->b2, &id2, 192);
     }
-    if (c->c_hi == c->c_lo) memcpy(&out->c, &id1, 96);
     if (c->h_hi == c->h_lo) memcpy(&out->h, &id1, 96);
     if (tm) {
       cudaEventSynchronize(c->ev_q);
