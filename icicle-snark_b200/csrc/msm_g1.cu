@@ -23,9 +23,14 @@ namespace b200 {
       // every window folded into one bucket set by precomputed bases: the reduction is 1/W of the work,
       // so wider windows (fewer adds per scalar) pay
       if (c < 2) c = 2;
-      int w0 = (bitsize + 2 + c - 1) / c;
-      // (small inputs: more, shorter buckets so that one thread per bucket still fills the machine)
-      if (factor >= w0 && w0 > 1 && lg >= 12) c = lg + 1 < 21 ? lg + 1 : 21;
+      if (factor > 1 && lg >= 12) {
+        // precomputed multiples fold the windows into few bucket sets, so the reduction is cheap and wider windows
+        // (fewer adds per scalar) pay; small inputs additionally want many short buckets so that one thread per
+        // bucket fills the machine. Prefer a width whose window count fits the factor (a single bucket set).
+        int c_fit = (bitsize + 2 + factor - 1) / factor; // smallest c with windows <= factor
+        int c_wide = lg + 1 < 21 ? lg + 1 : 21;
+        if (c_fit <= 21) c = c_wide > c_fit ? c_wide : c_fit;
+      }
       // a top window holding only 1..4 bits of the scalar funnels n/2^bits entries into each of a few
       // buckets; step down until the top window is either empty or reasonably wide
       while (c > 2) {
