@@ -15,7 +15,11 @@
 //                                               are folded by a second small kernel
 //   projective RCB adds (12M+)                  XYZZ buckets, affine bases: 8M+2S per accumulate step
 //   log-halving reduction (:846-942)            chunked running sums, one CTA tree per window, Horner over windows
-//   precompute_factor (:29-43)                  same table layout out[i*f+j] = 2^(shift*j) P_i
+//   precompute_factor (:29-43)                  same table layout out[i*f+j] = 2^(shift*j) P_i; window width chosen so the
+//                                               windows fit the factor (one bucket set, no Horner tail)
+//   one sort per MSM                            the sort (msm_sort.cu) is group-independent and can feed several
+//                                               accumulate/reduce phases sharing the scalars: the prover's A, B1, C
+//                                               run as ONE three-table G1 launch, B2 reuses the same sort
 #pragma once
 #include "common.cuh"
 #include "curve.cuh"
