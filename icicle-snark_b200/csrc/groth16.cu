@@ -105,10 +105,11 @@ namespace b200 {
   }
 
   // h[i] = from_mont(a[i]*b[i] - c[i])  (proof_helper.rs:153-167, plus the conversion the MSM digits need)
-  static __global__ void __launch_bounds__(256) quotient_combine_kernel(const Fr* d, uint32_t N, Fr* h)
+  static __global__ void __launch_bounds__(256)
+    quotient_combine_kernel(const Fr* a, const Fr* b, const Fr* c, uint32_t count, Fr* h)
   {
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) {
-      Fr v = ld_fp_coherent(d + i) * ld_fp_coherent(d + N + i) - ld_fp_coherent(d + 2 * (size_t)N + i);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
+      Fr v = ld_fp_coherent(a + i) * ld_fp_coherent(b + i) - ld_fp_coherent(c + i);
       st_fr(h + i, Fr::from_mont(v));
     }
   }
@@ -155,7 +156,7 @@ struct b200_zkey_cache {
   Fr *d_witness = nullptr, *d_vec = nullptr, *d_h = nullptr;
   uint8_t* d_results = nullptr; // 4 x G1 projective + 1 x G2 projective
   uint8_t* h_results = nullptr; // pinned
-  cudaStream_t s_copy = nullptr, s_g1 = nullptr, s_b1 = nullptr, s_c = nullptr, s_g2 = nullptr, s_q = nullptr;
+  cudaStream_t s_copy = nullptr, s_g1 = nullptr, s_g2 = nullptr, s_q = nullptr;
   cudaEvent_t ev_wit = nullptr, ev_start = nullptr, ev_h2d = nullptr, ev_r1cs = nullptr, ev_ntt = nullptr, ev_g1 = nullptr,
               ev_g2 = nullptr, ev_q = nullptr, ev_prev = nullptr, ev_b1 = nullptr, ev_c = nullptr;
   std::mutex mu;
@@ -187,7 +188,7 @@ namespace b200 {
     for (void* p : ptrs)
       if (p) cudaFree(p);
     if (c->h_results) cudaFreeHost(c->h_results);
-    cudaStream_t ss[] = {c->s_copy, c->s_g1, c->s_b1, c->s_c, c->s_g2, c->s_q};
+    cudaStream_t ss[] = {c->s_copy, c->s_g1, c->s_g2, c->s_q};
     for (auto s : ss)
       if (s) cudaStreamDestroy(s);
     cudaEvent_t es[] = {c->ev_wit, c->ev_start, c->ev_h2d, c->ev_r1cs, c->ev_ntt, c->ev_g1, c->ev_g2, c->ev_q, c->ev_prev, c->ev_b1, c->ev_c};
@@ -307,8 +308,6 @@ namespace b200 {
     CK(cudaStreamCreateWithPriority(&c->s_q, cudaStreamNonBlocking, use_prio ? prio_hi : prio_lo));
     CK(cudaStreamCreateWithPriority(&c->s_g2, cudaStreamNonBlocking, use_prio && prio_hi + 1 <= prio_lo ? prio_hi + 1 : prio_lo));
     CK(cudaStreamCreateWithPriority(&c->s_g1, cudaStreamNonBlocking, prio_lo));
-    CK(cudaStreamCreateWithPriority(&c->s_b1, cudaStreamNonBlocking, prio_lo));
-    CK(cudaStreamCreateWithPriority(&c->s_c, cudaStreamNonBlocking, prio_lo));
     for (cudaEvent_t* e : {&c->ev_wit, &c->ev_prev, &c->ev_b1, &c->ev_c})
       CK(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
     for (cudaEvent_t* e : {&c->ev_start, &c->ev_h2d, &c->ev_r1cs, &c->ev_ntt, &c->ev_g1, &c->ev_g2, &c->ev_q})
@@ -411,17 +410,23 @@ namespace b200 {
   }
 
   // ---------------------------------------------------------------------------------------------- prove
-  // enqueue everything up to the device-to-host copy of the five partial sums; returns without waiting
-  static eIcicleError commit_enqueue(b200_zkey_cache* c, const bn254_scalar_t* witness, uint32_t n_witness)
+  struct ResultSlots {
+    G1Projective *a, *b1, *c, *h;
+    G2Projective* b2;
+  };
+  static ResultSlots result_slots(b200_zkey_cache* c)
+  {
+    G1Projective* r_a = (G1Projective*)c->d_results;
+    return {r_a, r_a + 1, r_a + 2, r_a + 3, (G2Projective*)(c->d_results + 4 * 96)};
+  }
+
+  // witness H2D (proof_helper.rs:194-196); every compute stream waits on it
+  // (full == false: a rank that evaluates no R1CS rows only needs the witness slice its MSM shard reads)
+  static eIcicleError enqueue_upload(b200_zkey_cache* c, const bn254_scalar_t* witness, uint32_t n_witness, bool full = true)
   {
     if (!c || !witness) return ICICLE_INVALID_POINTER;
     if (n_witness != c->n_vars) return ICICLE_INVALID_ARGUMENT; // "Invalid witness length" (proof_helper.rs:259-264)
     B200_CUDA(cudaSetDevice(c->device), ICICLE_INVALID_DEVICE);
-    const uint32_t N = c->domain_size;
-    G1Projective* r_a = (G1Projective*)c->d_results;
-    G1Projective *r_b1 = r_a + 1, *r_c = r_a + 2, *r_h = r_a + 3;
-    G2Projective* r_b2 = (G2Projective*)(c->d_results + 4 * 96);
-
     // CacheManager::get_cache re-initialises the NTT domain on every proof (cache.rs:242-256): a no-op unless
     // someone released or shrank it in between
     {
@@ -429,41 +434,60 @@ namespace b200 {
       if (d && d->max_log < (int)c->power) bn254_ntt_release_domain();
       if (!d || d->max_log < (int)c->power) B200_TRY(ntt_init_domain_host(host_omega((int)c->power), c->s_copy));
     }
-
-    // witness H2D (proof_helper.rs:194-196); everything else waits on it
     B200_CUDA(cudaEventRecord(c->ev_start, c->s_copy), ICICLE_UNKNOWN_FALLBACK);
-    B200_CUDA(
-      cudaMemcpyAsync(c->d_witness, witness, (size_t)c->n_vars * 32, cudaMemcpyDefault, c->s_copy), ICICLE_COPY_FAILED);
+    const size_t w_lo = full ? 0 : c->a_lo, w_hi = full ? c->n_vars : c->a_hi;
+    if (w_hi > w_lo)
+      B200_CUDA(
+        cudaMemcpyAsync(c->d_witness + w_lo, witness + w_lo, (w_hi - w_lo) * 32, cudaMemcpyDefault, c->s_copy), ICICLE_COPY_FAILED);
     B200_CUDA(cudaEventRecord(c->ev_h2d, c->s_copy), ICICLE_UNKNOWN_FALLBACK);
-    for (cudaStream_t s : {c->s_g1, c->s_b1, c->s_c, c->s_g2, c->s_q})
+    for (cudaStream_t s : {c->s_g1, c->s_g2, c->s_q})
       B200_CUDA(cudaStreamWaitEvent(s, c->ev_h2d, 0), ICICLE_UNKNOWN_FALLBACK);
+    return ICICLE_SUCCESS;
+  }
 
-    // quotient chain + H on s_q
-    eIcicleError err = ICICLE_SUCCESS;
+  // A.w, B.w, A.w*B.w on s_q, then iNTT -> x keys -> NTT of polynomials [first, first+count) of the d_vec layout
+  // (0: B.w, 1: A.w, 2: their product) into `out` (count x N elements; may be d_vec + first*N itself)
+  static eIcicleError enqueue_quotient_polys(b200_zkey_cache* c, int first, int count, Fr* out)
+  {
+    const uint32_t N = c->domain_size;
     B200_LAUNCH(r1cs_eval_kernel, grid_for(N, 256, 8), 256, 0, c->s_q, c->row_ptr, c->col, c->val, c->d_witness, N, c->d_vec);
     cudaEventRecord(c->ev_r1cs, c->s_q);
-    if ((err = ntt_enqueue(c->d_vec, c->d_vec, (int)c->power, true, 3, false, c->keys, c->s_q)) != ICICLE_SUCCESS) return err;
-    if ((err = ntt_enqueue(c->d_vec, c->d_vec, (int)c->power, false, 3, false, nullptr, c->s_q)) != ICICLE_SUCCESS) return err;
-    B200_LAUNCH(quotient_combine_kernel, grid_for(N, 256, 8), 256, 0, c->s_q, c->d_vec, N, c->d_h);
-    cudaEventRecord(c->ev_ntt, c->s_q);
-    if (c->h_hi > c->h_lo) {
-      if ((err = msm_enqueue<Fq>(c->planH, c->d_h + c->h_lo, false, c->pH, r_h, c->s_q)) != ICICLE_SUCCESS) return err;
+    Fr* mine = c->d_vec + (size_t)first * N;
+    B200_TRY(ntt_enqueue(mine, mine, (int)c->power, true, count, false, c->keys, c->s_q));
+    return ntt_enqueue(mine, out, (int)c->power, false, count, false, nullptr, c->s_q);
+  }
+
+  // h = a.b - c over this rank's H shard (a, b, c point at the shard's first element), then the H MSM, on s_q
+  static eIcicleError enqueue_h(b200_zkey_cache* c, const Fr* a, const Fr* b, const Fr* cc)
+  {
+    const uint32_t cnt = c->h_hi - c->h_lo;
+    if (cnt) {
+      B200_LAUNCH(quotient_combine_kernel, grid_for(cnt, 256, 8), 256, 0, c->s_q, a, b, cc, cnt, c->d_h + c->h_lo);
+      cudaEventRecord(c->ev_ntt, c->s_q);
+      B200_TRY(msm_enqueue<Fq>(c->planH, c->d_h + c->h_lo, false, c->pH, result_slots(c).h, c->s_q));
+    } else {
+      cudaEventRecord(c->ev_ntt, c->s_q);
     }
     cudaEventRecord(c->ev_q, c->s_q);
+    return ICICLE_SUCCESS;
+  }
 
-    // witness-only MSMs (proof_helper.rs:198-206): A, B1, C and B2 take the same scalars over signal-indexed point
-    // tables, so ONE digit decomposition + counting sort feeds one G1 accumulate/reduce over three tables (s_g1) and
-    // one G2 accumulate/reduce (s_g2)
+  // witness-only MSMs (proof_helper.rs:198-206): A, B1, C and B2 take the same scalars over signal-indexed point
+  // tables, so ONE digit decomposition + counting sort feeds one G1 accumulate/reduce over three tables (s_g1) and
+  // one G2 accumulate/reduce (s_g2)
+  static eIcicleError enqueue_witness_msms(b200_zkey_cache* c)
+  {
+    ResultSlots r = result_slots(c);
     const Fr* w = c->d_witness;
     if (c->a_hi > c->a_lo) {
       MsmSorted sorted;
-      if ((err = msm_sort_enqueue(c->planA, w + c->a_lo, false, &sorted, c->s_g1)) != ICICLE_SUCCESS) return err;
+      B200_TRY(msm_sort_enqueue(c->planA, w + c->a_lo, false, &sorted, c->s_g1));
       cudaEventRecord(c->ev_b1, c->s_g1); // sort done
       cudaStreamWaitEvent(c->s_g2, c->ev_b1, 0);
       const G1Affine* g1_tables[3] = {c->pA, c->pB1, c->pC};
       const G2Affine* g2_tables[1] = {c->pB2};
-      if ((err = msm_reduce_enqueue<Fq>(c->planA, sorted, g1_tables, 3, r_a, c->s_g1)) != ICICLE_SUCCESS) return err;
-      if ((err = msm_reduce_enqueue<Fq2>(c->planB2, sorted, g2_tables, 1, r_b2, c->s_g2)) != ICICLE_SUCCESS) return err;
+      B200_TRY(msm_reduce_enqueue<Fq>(c->planA, sorted, g1_tables, 3, r.a, c->s_g1));
+      B200_TRY(msm_reduce_enqueue<Fq2>(c->planB2, sorted, g2_tables, 1, r.b2, c->s_g2));
       cudaEventRecord(c->ev_g2, c->s_g2);
       cudaStreamWaitEvent(c->s_g1, c->ev_g2, 0); // the sort's scratch is released after both consumers
       msm_sorted_free(&sorted, c->s_g1);
@@ -471,14 +495,29 @@ namespace b200 {
       cudaEventRecord(c->ev_g2, c->s_g2);
     }
     cudaEventRecord(c->ev_g1, c->s_g1);
+    return ICICLE_SUCCESS;
+  }
 
-    // join on s_copy, one D2H of the five partial sums
+  // join on s_copy, one D2H of the five partial sums
+  static eIcicleError enqueue_join(b200_zkey_cache* c)
+  {
     for (cudaEvent_t e : {c->ev_q, c->ev_g1, c->ev_g2})
       B200_CUDA(cudaStreamWaitEvent(c->s_copy, e, 0), ICICLE_UNKNOWN_FALLBACK);
     B200_CUDA(
       cudaMemcpyAsync(c->h_results, c->d_results, 4 * 96 + 192, cudaMemcpyDeviceToHost, c->s_copy), ICICLE_COPY_FAILED);
     B200_CUDA(cudaEventRecord(c->ev_prev, c->s_copy), ICICLE_UNKNOWN_FALLBACK);
     return ICICLE_SUCCESS;
+  }
+
+  // enqueue everything up to the device-to-host copy of the five partial sums; returns without waiting
+  static eIcicleError commit_enqueue(b200_zkey_cache* c, const bn254_scalar_t* witness, uint32_t n_witness)
+  {
+    B200_TRY(enqueue_upload(c, witness, n_witness));
+    const uint32_t N = c->domain_size;
+    B200_TRY(enqueue_quotient_polys(c, 0, 3, c->d_vec)); // quotient chain + H on the (higher-priority) s_q
+    B200_TRY(enqueue_h(c, c->d_vec + c->h_lo, c->d_vec + N + c->h_lo, c->d_vec + 2 * (size_t)N + c->h_lo));
+    B200_TRY(enqueue_witness_msms(c));
+    return enqueue_join(c);
   }
 
   static eIcicleError commit_wait(b200_zkey_cache* c, b200_groth16_partials* out, b200_prove_timings* tm)
@@ -512,6 +551,7 @@ namespace b200 {
       tm->msm_g1_ms = t_g1;
       tm->msm_g2_ms = t_g2;
       tm->total_ms = std::max(t_q, std::max(t_g1, t_g2));
+      (void)cudaGetLastError(); // timing queries must never poison the next call
     }
     return ICICLE_SUCCESS;
   }
@@ -737,6 +777,40 @@ eIcicleError b200_groth16_commit_partials(
   b200_zkey_cache* cache, const bn254_scalar_t* witness, uint32_t n_witness, b200_groth16_partials* out, b200_prove_timings* tm)
 {
   return commit_partials(cache, witness, n_witness, out, tm);
+}
+
+eIcicleError b200_groth16_commit_begin(
+  b200_zkey_cache* c, const bn254_scalar_t* witness, uint32_t n_witness, int first_poly, int poly_count, void* out_dev)
+{
+  if (!c || (poly_count > 0 && !out_dev)) return ICICLE_INVALID_POINTER;
+  if (first_poly < 0 || poly_count < 0 || first_poly + poly_count > 3) return ICICLE_INVALID_ARGUMENT;
+  c->mu.lock();
+  eIcicleError e = enqueue_upload(c, witness, n_witness, poly_count > 0);
+  if (e == ICICLE_SUCCESS && poly_count > 0) e = enqueue_quotient_polys(c, first_poly, poly_count, (Fr*)out_dev);
+  if (e == ICICLE_SUCCESS && poly_count == 0) cudaEventRecord(c->ev_r1cs, c->s_q); // keep the phase timers well-defined
+  if (e == ICICLE_SUCCESS) e = enqueue_witness_msms(c); // keep the GPU busy while the caller exchanges slices
+  if (e == ICICLE_SUCCESS && cudaStreamSynchronize(c->s_q) != cudaSuccess) e = ICICLE_SYNCHRONIZATION_FAILED;
+  if (e != ICICLE_SUCCESS) c->mu.unlock(); // otherwise held until commit_end
+  return e;
+}
+
+eIcicleError b200_groth16_commit_end(
+  b200_zkey_cache* c, const void* a_dev, const void* b_dev, const void* c_dev, b200_groth16_partials* out, b200_prove_timings* tm)
+{
+  if (!c || !a_dev || !b_dev || !c_dev || !out) return ICICLE_INVALID_POINTER;
+  eIcicleError e = enqueue_h(c, (const Fr*)a_dev, (const Fr*)b_dev, (const Fr*)c_dev);
+  if (e == ICICLE_SUCCESS) e = enqueue_join(c);
+  if (e == ICICLE_SUCCESS) e = commit_wait(c, out, tm);
+  c->mu.unlock();
+  return e;
+}
+
+eIcicleError b200_zkey_cache_h_range(const b200_zkey_cache* c, uint32_t* lo, uint32_t* hi)
+{
+  if (!c || !lo || !hi) return ICICLE_INVALID_POINTER;
+  *lo = c->h_lo;
+  *hi = c->h_hi;
+  return ICICLE_SUCCESS;
 }
 
 eIcicleError b200_groth16_finish(

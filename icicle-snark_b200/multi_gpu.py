@@ -33,3 +33,49 @@ def all_gather_partials(parts: Groth16Partials, device="cpu"):
     dist.all_gather(out, mine)
     host = torch.stack(out).cpu().numpy()
     return [Groth16Partials.from_buffer_copy(np.ascontiguousarray(host[i]).tobytes()) for i in range(world)]
+
+
+# ---- quotient split (include/icicle_b200.h: b200_groth16_commit_begin / commit_end) ----------------------------
+def poly_owner(j: int, world: int) -> int:
+    """Rank that transforms polynomial j of (0: B.w, 1: A.w, 2: A.w*B.w); owned sets are contiguous."""
+    if world >= 3:
+        return j
+    if world == 2:
+        return 0 if j < 2 else 1
+    return 0
+
+
+def owned_polys(rank: int, world: int):
+    mine = [j for j in range(3) if poly_owner(j, world) == rank]
+    return (mine[0], len(mine)) if mine else (0, 0)
+
+
+class QuotientExchange:
+    """Buffers + the one collective step of the split: every owner scatters the H-shard slices of its transformed
+    polynomial(s); afterwards each rank holds its slice of all three."""
+
+    def __init__(self, cache, device):
+        import torch
+        import torch.distributed as dist
+        self.cache, self.dist, self.torch = cache, dist, torch
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        self.N = cache.domain_size
+        self.first, self.count = owned_polys(self.rank, self.world)
+        self.mine = torch.empty((max(self.count, 1), self.N, 8), dtype=torch.int32, device=device)
+        self.ranges = [shard_range(self.N, r, self.world) for r in range(self.world)]
+        lo, hi = self.ranges[self.rank]
+        assert (lo, hi) == cache.h_range()
+        self.slices = torch.empty((3, hi - lo, 8), dtype=torch.int32, device=device)
+
+    def commit(self, witness, n_witness=None):
+        self.cache.commit_begin(witness, self.first, self.count, self.mine.data_ptr(), n_witness=n_witness)
+        for j in range(3):
+            owner = poly_owner(j, self.world)
+            sl = None
+            if self.rank == owner:
+                src = self.mine[j - self.first]
+                sl = [src[lo:hi] for lo, hi in self.ranges]
+            self.dist.scatter(self.slices[j], scatter_list=sl, src=owner)
+        self.torch.cuda.current_stream().synchronize()
+        # d_vec order: 0 = B.w', 1 = A.w', 2 = product'; commit_end takes (a, b, c) = (A', B', product')
+        return self.cache.commit_end(self.slices[1].data_ptr(), self.slices[0].data_ptr(), self.slices[2].data_ptr())

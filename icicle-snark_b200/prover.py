@@ -67,6 +67,23 @@ class ZKeyCache:
               "b200_groth16_commit_partials")
         return parts, tm
 
+    def h_range(self):
+        lo, hi = C.c_uint32(), C.c_uint32()
+        check(self.lib.dll.b200_zkey_cache_h_range(self.handle, C.byref(lo), C.byref(hi)))
+        return lo.value, hi.value
+
+    def commit_begin(self, witness, first_poly, poly_count, out_dev_ptr, n_witness=None):
+        """N > 1 quotient split, phase 1 (see include/icicle_b200.h)."""
+        wp, n = self._wptr(witness, n_witness)
+        check(self.lib.dll.b200_groth16_commit_begin(self.handle, wp, C.c_uint32(n), C.c_int(first_poly), C.c_int(poly_count),
+                                                     C.c_void_p(out_dev_ptr)), "b200_groth16_commit_begin")
+
+    def commit_end(self, a_dev_ptr, b_dev_ptr, c_dev_ptr):
+        parts, tm = Groth16Partials(), ProveTimings()
+        check(self.lib.dll.b200_groth16_commit_end(self.handle, C.c_void_p(a_dev_ptr), C.c_void_p(b_dev_ptr), C.c_void_p(c_dev_ptr),
+                                                   C.byref(parts), C.byref(tm)), "b200_groth16_commit_end")
+        return parts, tm
+
     def finish(self, parts_list, r=None, s=None):
         arr = (Groth16Partials * len(parts_list))(*parts_list)
         proof = Groth16Proof()

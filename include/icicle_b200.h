@@ -276,6 +276,18 @@ eIcicleError b200_zkey_cache_create_sharded(const uint8_t* zkey, size_t zkey_len
 eIcicleError b200_groth16_commit_partials(b200_zkey_cache* cache, const bn254_scalar_t* witness,
                                           uint32_t n_witness, b200_groth16_partials* out,
                                           b200_prove_timings* timings);
+/* Quotient split for N > 1 ranks (optional; commit_partials replicates the chain instead): the three polynomials
+ * (0: B.w, 1: A.w, 2: A.w*B.w; src/proof_helper.rs:94-147) are independent, so rank k transforms polynomials
+ * [first_poly, first_poly+poly_count) into out_dev (poly_count x domain_size elements, DEVICE memory), the ranks
+ * exchange the slices of their H shard (b200_zkey_cache_h_range) with one collective, and commit_end consumes this
+ * rank's slice of each (a = A.w', b = B.w', c = product', DEVICE pointers to the shard's first element).
+ * commit_begin also uploads the witness and starts the witness-only MSMs, which run during the exchange.
+ * The cache is locked from a successful commit_begin until commit_end returns. */
+eIcicleError b200_groth16_commit_begin(b200_zkey_cache* cache, const bn254_scalar_t* witness, uint32_t n_witness,
+                                       int first_poly, int poly_count, void* out_dev);
+eIcicleError b200_groth16_commit_end(b200_zkey_cache* cache, const void* a_dev, const void* b_dev, const void* c_dev,
+                                     b200_groth16_partials* out, b200_prove_timings* timings);
+eIcicleError b200_zkey_cache_h_range(const b200_zkey_cache* cache, uint32_t* lo, uint32_t* hi);
 eIcicleError b200_groth16_finish(const b200_zkey_cache* cache, const b200_groth16_partials* parts, int n_parts,
                                  const bn254_scalar_t* r, const bn254_scalar_t* s, b200_groth16_proof* proof);
 

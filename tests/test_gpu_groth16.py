@@ -159,3 +159,30 @@ def test_full_size_proof_verifies_under_reference_pairing(gpu, ref):
         assert not G.verify(ref, pkg.proof_to_dict(p1), [public[0] ^ 1], vk)
     finally:
         cache.close()
+
+
+def test_quotient_split_api_single_rank(gpu):
+    """commit_begin / commit_end (the N > 1 quotient split) driven on one device: all three polynomials transformed
+    into a caller buffer, slices handed back, same proof as the fused path."""
+    import torch
+    zkey, wtns, vk, gold11, goldrs, _ = load(100)
+    w = wtns_words(wtns)
+    cache = pkg.ZKeyCache(gpu, zkey)
+    try:
+        N = cache.domain_size
+        lo, hi = cache.h_range()
+        assert (lo, hi) == (0, N)
+        buf = torch.empty((3, N, 8), dtype=torch.int32, device="cuda")
+        cache.commit_begin(w, 0, 3, buf.data_ptr())
+        parts, tm = cache.commit_end(buf[1].data_ptr(), buf[0].data_ptr(), buf[2].data_ptr())
+        proof = cache.finish([parts], FIXED_R, FIXED_S)
+        assert pkg.proof_json(proof) == goldrs
+        # a rank that owns no polynomial (world > 3): poly_count = 0, slices come from the other ranks
+        cache.commit_begin(w, 0, 0, buf.data_ptr())
+        parts0, _ = cache.commit_end(buf[1].data_ptr(), buf[0].data_ptr(), buf[2].data_ptr())
+        assert pkg.proof_json(cache.finish([parts0], FIXED_R, FIXED_S)) == goldrs
+        # the regular path still works afterwards (lock released)
+        p2, _ = cache.prove(w, 1, 1)
+        assert pkg.proof_json(p2) == gold11
+    finally:
+        cache.close()
