@@ -264,6 +264,182 @@ namespace b200 {
     }
   }
 
+
+  // ---- FP64-pipe candidate: 6 x 48-bit limbs held as exact-integer doubles, Montgomery R = 2^288.
+  // Every partial product x*y (< 2^96) is added to its column with a fixed-exponent chain:
+  //   s' = fma_rz(x, y, s)            s in [2^100, 2^101): keeps the multiples of 2^48 (ulp), drops r = (s + xy) - s'
+  //   r  = fma(x, y, s - s')          exact, in [0, 2^48)
+  //   l += r                          exact while l < 2^53 (12 terms + carry)
+  // so a column is (s - 2^100) + l with NO integer instructions: the multiplier lives on the FP64 pipe, which the
+  // integer kernels leave idle and which co-issues with IMAD at full rate (mode 4).
+  struct D48 {
+    double v[6];
+  };
+  __device__ __forceinline__ void d48_addprod(double& s, double& l, double x, double y)
+  {
+    double sn = __fma_rz(x, y, s);
+    double d = __dsub_rn(s, sn);
+    double r = __fma_rn(x, y, d);
+    l = __dadd_rn(l, r);
+    s = sn;
+  }
+  __device__ __forceinline__ D48 mul48(const D48& a, const D48& b)
+  {
+    const double C100 = 1267650600228229401496703205376.0;  // 2^100
+    const double I48 = 3.552713678800501e-15;               // 2^-48
+    const double NINV = (double)0x782e4866389ull;           // -q^-1 mod 2^48
+    const double PL[6] = {(double)0x8c16d87cfd47ull, (double)0x6871ca8d3c20ull, (double)0x585d97816a91ull,
+                          (double)0xb85045b68181ull, (double)0x4e72e131a029ull, (double)0x3064ull};
+    double s[12], l[12];
+#pragma unroll
+    for (int k = 0; k < 12; ++k) {
+      s[k] = C100;
+      l[k] = 0.0;
+    }
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+#pragma unroll
+      for (int j = 0; j < 6; ++j)
+        d48_addprod(s[i + j], l[i + j], a.v[j], b.v[i]);
+      double u = __dadd_rz(l[i], C100);
+      double tl = __dsub_rn(l[i], __dsub_rn(u, C100)); // low 48 bits of the column
+      double hq = __fma_rz(tl, NINV, C100);
+      double q = __fma_rn(tl, NINV, __dsub_rn(C100, hq)); // tl * n' mod 2^48
+#pragma unroll
+      for (int j = 0; j < 6; ++j)
+        d48_addprod(s[i + j], l[i + j], q, PL[j]);
+      double carry = __fma_rn(l[i], I48, __dmul_rn(__dsub_rn(s[i], C100), I48));
+      l[i + 1] = __dadd_rn(l[i + 1], carry);
+    }
+    D48 r;
+#pragma unroll
+    for (int k = 6; k < 12; ++k) {
+      double u = __dadd_rz(l[k], C100);
+      double hi = __dsub_rn(u, C100);
+      r.v[k - 6] = __dsub_rn(l[k], hi);
+      if (k < 11) {
+        double carry = __fma_rn(hi, I48, __dmul_rn(__dsub_rn(s[k], C100), I48));
+        l[k + 1] = __dadd_rn(l[k + 1], carry);
+      }
+    }
+    return r;
+  }
+  __device__ __forceinline__ D48 to48(const Fq& x)
+  {
+    D48 r;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+      int bit = 48 * k, w = bit >> 5, sh = bit & 31; // sh is 0 or 16
+      uint64_t lo = x.v[w], mid = w + 1 < 8 ? x.v[w + 1] : 0, top = w + 2 < 8 ? x.v[w + 2] : 0;
+      uint64_t val = sh == 0 ? (lo | ((mid & 0xffffull) << 32)) : ((lo >> 16) | (mid << 16));
+      (void)top;
+      val &= 0xffffffffffffull;
+      r.v[k] = __longlong_as_double((long long)(val | 0x4330000000000000ull)) - 4503599627370496.0;
+    }
+    return r;
+  }
+  __device__ __forceinline__ Fq from48(const D48& x) // limbs normalised (< 2^48), value < 2^256
+  {
+    uint64_t l[6];
+#pragma unroll
+    for (int k = 0; k < 6; ++k)
+      l[k] = (uint64_t)__double_as_longlong(x.v[k] + 4503599627370496.0) & 0xffffffffffffull;
+    Fq r;
+    r.v[0] = (uint32_t)l[0];
+    r.v[1] = (uint32_t)(l[0] >> 32) | (uint32_t)(l[1] << 16);
+    r.v[2] = (uint32_t)(l[1] >> 16);
+    r.v[3] = (uint32_t)l[2];
+    r.v[4] = (uint32_t)(l[2] >> 32) | (uint32_t)(l[3] << 16);
+    r.v[5] = (uint32_t)(l[3] >> 16);
+    r.v[6] = (uint32_t)l[4];
+    r.v[7] = (uint32_t)(l[4] >> 32) | (uint32_t)(l[5] << 16);
+    return r;
+  }
+
+  // self-check: 2^32 * mul48(a,b) == CIOS(a,b) mod q  (R = 2^288 vs 2^256)
+  __global__ void mul48_check_kernel(uint32_t seed, int* bad)
+  {
+    uint32_t st = seed + blockIdx.x * 977u + threadIdx.x * 131u;
+    Fq a, b;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      st = st * 1664525u + 1013904223u;
+      a.v[i] = st;
+      st = st * 1664525u + 1013904223u;
+      b.v[i] = st;
+    }
+    a.v[7] &= 0x1fffffffu;
+    b.v[7] &= 0x1fffffffu;
+    if (threadIdx.x == 0) { // edge: q - 1
+      for (int i = 0; i < 8; ++i)
+        a.v[i] = FqCfg::P(i);
+      a.v[0] -= 1;
+    }
+    Fq want = a * b;
+    Fq got = from48(mul48(to48(a), to48(b)));
+    Fq zero = Fq::zero();
+    got = got + zero; // < 2q -> canonical
+    for (int k = 0; k < 32; ++k)
+      got = got.dbl();
+    // and a dependent chain through the FP64 representation
+    D48 x = to48(a), y = to48(b);
+    Fq w2 = a;
+    for (int k = 0; k < 5; ++k) {
+      x = mul48(x, y);
+      w2 = w2 * b;
+    }
+    Fq g2 = from48(x) + zero;
+    for (int k = 0; k < 160; ++k)
+      g2 = g2.dbl();
+    if (got != want || g2 != w2) atomicAdd(bad, 1);
+  }
+
+  // 10: FP64 multiplier alone; 11: co-issue test - 256-thread CTAs, warps 0-3 run the integer CIOS (3/2 x the
+  // iterations, matching its speed) and warps 4-7 the FP64 multiplier, so every SM sub-partition (warp id mod 4)
+  // holds both kinds
+  template <int MODE>
+  __global__ void __launch_bounds__(256) fieldmul48_kernel(uint32_t* out, int iters, uint32_t seed)
+  {
+    const bool use_fp = MODE == 10 || ((threadIdx.x >> 7) & 1);
+    if (MODE == 11 && !use_fp) iters = iters * 3 / 2;
+    Fq x[4], y;
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        x[k].v[i] = (threadIdx.x * 2654435761u + seed + i * 40503u + k) & 0x0fffffffu;
+    y = x[0];
+    uint32_t sacc = 0;
+    if (use_fp) {
+      D48 dx[4], dy = to48(y);
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        dx[k] = to48(x[k]);
+      for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          dx[k] = mul48(dx[k], dy);
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+#pragma unroll
+        for (int i = 0; i < 6; ++i)
+          sacc ^= (uint32_t)__double_as_longlong(dx[k].v[i]);
+    } else {
+      for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          x[k] = x[k] * y;
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          sacc ^= x[k].v[i];
+    }
+    if (sacc == 0x12345678u) out[0] = sacc;
+  }
+
   // mode 9: "carry-save" wide multiply-add: IMAD.WIDE with carry-OUT only (no carry-in) + a counter bumped by the
   // carry on the ALU pipe - the building block of a multiplier without IMAD.WIDE.X chains
   __global__ void __launch_bounds__(256) carrysave_kernel(uint64_t* out, int iters, uint32_t seed)
@@ -329,6 +505,22 @@ extern "C" double b200_pipe_peak(int mode)
       if (r9 > best) best = r9;
       continue;
     }
+    if (mode == 10 || mode == 11) {
+      const int it2 = 256, bl2 = sm_count() * 4;
+      if (mode == 10)
+        fieldmul48_kernel<10><<<bl2, 256>>>((uint32_t*)d, it2, rep);
+      else
+        fieldmul48_kernel<11><<<bl2, 256>>>((uint32_t*)d, it2, rep);
+      cudaEventRecord(e1, 0);
+      if (cudaEventSynchronize(e1) != cudaSuccess) break;
+      float msx = 0;
+      cudaEventElapsedTime(&msx, e0, e1);
+      // mode 11: half the threads do it2*3/2 iterations, half it2
+      double per_thread = mode == 10 ? (double)it2 * 4 : ((double)(it2 * 3 / 2) + it2) * 4 / 2;
+      double rx = (double)bl2 * 256 * per_thread / (msx * 1e-3);
+      if (rx > best) best = rx;
+      continue;
+    }
     if (mode >= 6) {
       const int it2 = 512, bl2 = sm_count() * 8;
       if (mode == 6)
@@ -375,6 +567,63 @@ extern "C" int b200_mul29_selfcheck(void)
   if (cudaMalloc((void**)&d, 4) != cudaSuccess) return -1;
   cudaMemset(d, 0, 4);
   mul29_check_kernel<<<64, 128>>>(12345u, d);
+  int h = -1;
+  cudaMemcpy(&h, d, 4, cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  return h;
+}
+
+// Co-residency test with separately compiled kernels (each keeps its own register budget), two streams:
+// returns rates (field products/s): out[0] integer CIOS alone, out[1] FP64 multiplier alone, out[2] both together.
+extern "C" int b200_corun_test(double* out3, int ctas_int_per_sm, int ctas_fp_per_sm)
+{
+  if (ensure_device() != ICICLE_SUCCESS) return -1;
+  uint32_t* d = nullptr;
+  if (cudaMalloc((void**)&d, 64) != cudaSuccess) return -1;
+  cudaStream_t sa, sb;
+  cudaStreamCreateWithFlags(&sa, cudaStreamNonBlocking);
+  cudaStreamCreateWithFlags(&sb, cudaStreamNonBlocking);
+  cudaEvent_t e0, ea, eb;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&ea);
+  cudaEventCreate(&eb);
+  const int ga = sm_count() * ctas_int_per_sm, gb = sm_count() * ctas_fp_per_sm;
+  const int ita = 1536, itb = 1024; // ~ equal duration alone at 4:2 CTAs
+  for (int mode = 0; mode < 3; ++mode) {
+    double best = 0;
+    for (int rep = 0; rep < 3; ++rep) {
+      cudaDeviceSynchronize();
+      cudaEventRecord(e0, sa);
+      cudaStreamWaitEvent(sb, e0, 0);
+      if (mode != 1) fieldmul_kernel<6><<<ga, 128, 0, sa>>>(d, ita, rep);
+      if (mode != 0) fieldmul48_kernel<10><<<gb, 128, 0, sb>>>(d, itb, rep);
+      cudaEventRecord(ea, sa);
+      cudaEventRecord(eb, sb);
+      cudaEventSynchronize(ea);
+      cudaEventSynchronize(eb);
+      float ta = 0, tb = 0;
+      cudaEventElapsedTime(&ta, e0, ea);
+      cudaEventElapsedTime(&tb, e0, eb);
+      float t = ta > tb ? ta : tb;
+      double muls = (mode != 1 ? (double)ga * 128 * ita * 4 : 0) + (mode != 0 ? (double)gb * 128 * itb * 4 : 0);
+      double r = muls / (t * 1e-3);
+      if (r > best) best = r;
+    }
+    out3[mode] = best;
+  }
+  cudaFree(d);
+  cudaStreamDestroy(sa);
+  cudaStreamDestroy(sb);
+  return 0;
+}
+
+extern "C" int b200_mul48_selfcheck(void)
+{
+  if (ensure_device() != ICICLE_SUCCESS) return -1;
+  int* d = nullptr;
+  if (cudaMalloc((void**)&d, 4) != cudaSuccess) return -1;
+  cudaMemset(d, 0, 4);
+  mul48_check_kernel<<<64, 128>>>(777u, d);
   int h = -1;
   cudaMemcpy(&h, d, 4, cudaMemcpyDeviceToHost);
   cudaFree(d);
