@@ -221,7 +221,7 @@ namespace b200 {
   template <int MODE>
   __global__ void __launch_bounds__(128) fieldmul_kernel(uint32_t* out, int iters, uint32_t seed)
   {
-    if (MODE == 6) {
+    if (MODE == 6 || MODE == 12 || MODE == 13) {
       Fq x[4], y;
 #pragma unroll
       for (int k = 0; k < 4; ++k)
@@ -231,8 +231,19 @@ namespace b200 {
       y = x[0];
       for (int it = 0; it < iters; ++it) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          x[k] = x[k] * y;
+        for (int k = 0; k < 4; ++k) {
+          if (MODE == 6) x[k] = x[k] * y;
+          #ifdef __CUDA_ARCH__
+          if (MODE == 12) x[k] = x[k].sqr_sos(); // dedicated squaring (36 + 72 wide MACs)
+#endif
+#ifdef __CUDA_ARCH__
+          if (MODE == 13) {                  // wide product + separate SOS reduction (64 + 72 wide MACs)
+            uint32_t T[16];
+            Fq::mul_wide(T, x[k].v, y.v);
+            x[k] = Fq::redc_wide(T);
+          }
+#endif
+        }
       }
       uint32_t s = 0;
 #pragma unroll
@@ -527,6 +538,10 @@ extern "C" double b200_pipe_peak(int mode)
         fieldmul_kernel<6><<<bl2, 128>>>((uint32_t*)d, it2, rep);
       else if (mode == 7)
         fieldmul_kernel<7><<<bl2, 128>>>((uint32_t*)d, it2, rep);
+      else if (mode == 12)
+        fieldmul_kernel<12><<<bl2, 128>>>((uint32_t*)d, it2, rep);
+      else if (mode == 13)
+        fieldmul_kernel<13><<<bl2, 128>>>((uint32_t*)d, it2, rep);
       else
         fieldmul_kernel<8><<<bl2, 128>>>((uint32_t*)d, it2, rep);
       cudaEventRecord(e1, 0);

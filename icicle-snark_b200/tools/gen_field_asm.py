@@ -150,6 +150,219 @@ def block_addp_masked(p):
     return ops, ins, [f"t{k}" for k in range(N)]
 
 
+
+# ----------------------------------------------------------------------------- wide (512-bit) products, SOS reduction
+# T = X + Y*2^32 with X[0..15] aligned at limb 0 and Y[0..15] aligned at limb 1 (same even/odd pairing as above, so every
+# mad.lo.cc/madc.hi.cc pair lands on an aligned register pair).  Used for lazy reduction in Fq2 (3 wide products, 2
+# reductions instead of 3) and for the dedicated squaring.
+W = 16
+
+
+def _row_targets(i):
+    """Row i adds x_j * b * 2^(32(i+j)), j = 0..7.  Returns (jlist, array, first limb index) for the two carry chains."""
+    if i % 2 == 0:
+        return ((0, 2, 4, 6), "X", i), ((1, 3, 5, 7), "Y", i)
+    return ((1, 3, 5, 7), "X", i + 1), ((0, 2, 4, 6), "Y", i - 1)
+
+
+def block_mulwide_row(i, first=False, src="A", const_limbs=None):
+    """(X,Y) += src * B * 2^(32 i); src = operand array A, or the modulus limbs as immediates (reduction row)."""
+    ins, used = [], set()
+    for jl, arr, base in _row_targets(i):
+        for k, j in enumerate(jl):
+            lo, hi = base + 2 * k, base + 2 * k + 1
+            a = h(const_limbs[j]) if const_limbs else f"{src}{j}"
+            if first:
+                ins.append(("mul.lo.u32", f"{arr}{lo}", a, "B"))
+                ins.append(("mul.hi.u32", f"{arr}{hi}", a, "B"))
+            else:
+                ins.append(("mad.lo.cc.u32" if k == 0 else "madc.lo.cc.u32", f"{arr}{lo}", a, "B", f"{arr}{lo}"))
+                ins.append(("madc.hi.cc.u32", f"{arr}{hi}", a, "B", f"{arr}{hi}"))
+            used.update((f"{arr}{lo}", f"{arr}{hi}"))
+        nxt = base + 8
+        if not first and nxt < W and const_limbs:
+            # reduction row: the limbs above the chain hold live data (an addc could wrap once in 2^32 calls), so the
+            # carry is counted in a separate word K[limb - 8] that redc16_final adds to the result
+            kidx = (nxt if arr == "X" else nxt + 1) - 8
+            ins.append(("addc.u32", f"K{kidx}", f"K{kidx}", "0"))
+            used.add(f"K{kidx}")
+        elif not first and nxt < W:
+            # product row on a zero-initialised accumulator: the pair above the chain holds at most earlier carries,
+            # one addc cannot overflow it
+            ins.append(("addc.u32", f"{arr}{nxt}", f"{arr}{nxt}", "0"))
+            used.add(f"{arr}{nxt}")
+        elif not first:
+            # chain ends at the top of the 16-limb accumulator: no carry can leave a < 2^512 value; close the chain
+            last = ins.pop()
+            ins.append((last[0].replace(".cc", ""),) + last[1:])
+    names = sorted(used, key=lambda n: (n[0], int(n[1:])))
+    ops = [(n, "=r" if first else "+r") for n in names]
+    if not const_limbs:
+        ops += [(f"{src}{j}", "r") for j in range(N)]
+    ops += [("B", "r")]
+    return ops, ins, []
+
+
+def _chain8(kind, outs, xs, ys, cin=None, cout=None):
+    """outs = xs (+|-) ys over 8 limbs with optional carry/borrow word in (0/1) and out (0/1)."""
+    add = kind == "add"
+    ins, temps = [], []
+    if cin is not None:
+        temps.append("tc")
+        # CC := cin  (0 + 0xffffffff carries iff cin == 1;  0 - cin borrows iff cin == 1)
+        ins.append(("add.cc.u32", "tc", cin, "0xffffffff") if add else ("sub.cc.u32", "tc", "0", cin))
+    for k in range(8):
+        first = k == 0 and cin is None
+        last = k == 7 and cout is None
+        base = ("add" if add else "sub") if first else ("addc" if add else "subc")
+        op = base + ("" if last else ".cc") + ".u32"
+        ins.append((op, outs[k], xs[k], ys[k]))
+    if cout is not None:
+        if add:
+            ins.append(("addc.u32", cout, "0", "0"))
+        else:
+            ins.append(("subc.u32", cout, "0", "0"))       # 0 or 0xffffffff
+            ins.append(("and.b32", cout, cout, "0x00000001"))
+    return ins, temps
+
+
+def block_merge16_lo():
+    """T[0..7] of X + Y*2^32 and the carry word CO into limb 8."""
+    ins = [("mov.u32", "T0", "X0")]
+    for k in range(1, 8):
+        ins.append(("add.cc.u32" if k == 1 else "addc.cc.u32", f"T{k}", f"X{k}", f"Y{k - 1}"))
+    ins.append(("addc.u32", "CO", "0", "0"))
+    ops = [(f"T{i}", "=r") for i in range(8)] + [("CO", "=r")] + [(f"X{i}", "r") for i in range(8)] + [(f"Y{i}", "r") for i in range(7)]
+    return ops, ins, []
+
+
+def block_merge16_hi():
+    """T[8..15] = X[8..15] + Y[7..14] + CI (the value is < 2^512: no carry leaves limb 15)."""
+    ins, temps = _chain8("add", [f"T{8 + k}" for k in range(8)], [f"X{8 + k}" for k in range(8)], [f"Y{7 + k}" for k in range(8)], cin="CI")
+    ops = [(f"T{8 + i}", "=r") for i in range(8)] + [(f"X{8 + i}", "r") for i in range(8)] + [(f"Y{7 + i}", "r") for i in range(8)] + [("CI", "r")]
+    return ops, ins, temps
+
+
+def block_addsub8(kind, with_cin, with_cout):
+    """R (+|-)= U over 8 limbs, carry/borrow words CI / CO as 0/1."""
+    ins, temps = _chain8(kind, [f"R{k}" for k in range(8)], [f"R{k}" for k in range(8)], [f"U{k}" for k in range(8)],
+                         cin="CI" if with_cin else None, cout="CO" if with_cout else None)
+    ops = [(f"R{i}", "+r") for i in range(8)]
+    if with_cout:
+        ops.append(("CO", "=r"))
+    ops += [(f"U{i}", "r") for i in range(8)]
+    if with_cin:
+        ops.append(("CI", "r"))
+    return ops, ins, temps
+
+
+def block_addconst8(c8, with_cin, with_cout):
+    """R += 8-limb constant, carry words as above."""
+    cl = [(c8 >> (32 * i)) & MASK for i in range(8)]
+    ins, temps = _chain8("add", [f"R{k}" for k in range(8)], [f"R{k}" for k in range(8)], [h(x) for x in cl],
+                         cin="CI" if with_cin else None, cout="CO" if with_cout else None)
+    ops = [(f"R{i}", "+r") for i in range(8)]
+    if with_cout:
+        ops.append(("CO", "=r"))
+    if with_cin:
+        ops.append(("CI", "r"))
+    return ops, ins, temps
+
+
+def block_redc16_step(i, p):
+    """One SOS reduction step on (X, Y, C): with all limbs below i already zero,
+    m = (X_i + Y_{i-1} + C mod 2^32) * (-p^-1);  (X,Y) += m * p * 2^(32 i);  C = carry of limb i into limb i+1."""
+    pl = limbs(p)
+    yi = f"Y{i - 1}" if i > 0 else "0"
+    ins = [("add.u32", "t", f"X{i}", yi), ("add.u32", "t", "t", "C"), ("mul.lo.u32", "B", "t", h(inv32(p)))]
+    _, row, _ = block_mulwide_row(i, const_limbs=pl)
+    ins += row
+    ins += [("add.cc.u32", "t", f"X{i}", yi), ("addc.u32", "c1", "0", "0"), ("add.cc.u32", "t", "t", "C"),
+            ("addc.u32", "C", "c1", "0")]
+    used = set()
+    for ins_ in ins:
+        for x in ins_[1:]:
+            if x and x[0] in "XYK" and x[1:].isdigit():
+                used.add(x)
+    names = sorted(used, key=lambda n: (n[0], int(n[1:])))
+    ops = [(n, "+r") for n in names] + [("C", "+r")]
+    return ops, ins, ["t", "B", "c1"]
+
+
+def block_redc16_final():
+    """R = X[8..15] + Y[7..14]  (the value / 2^256, still missing the carry word C; < 2p so nothing overflows)."""
+    ins = []
+    for k in range(N):
+        op = "add.cc.u32" if k == 0 else ("addc.cc.u32" if k < N - 1 else "addc.u32")
+        ins.append((op, f"R{k}", f"X{8 + k}", f"Y{7 + k}"))
+    ops = [(f"R{i}", "=r") for i in range(N)] + [(f"X{8 + i}", "r") for i in range(N)] + [(f"Y{7 + i}", "r") for i in range(N)]
+    return ops, ins, []
+
+
+def block_addk():
+    """R += K[0..7] (the carry words collected by the reduction rows)."""
+    ins = []
+    for k in range(N):
+        op = "add.cc.u32" if k == 0 else ("addc.cc.u32" if k < N - 1 else "addc.u32")
+        ins.append((op, f"R{k}", f"R{k}", f"K{k}"))
+    ops = [(f"R{i}", "+r") for i in range(N)] + [(f"K{i}", "r") for i in range(N)]
+    return ops, ins, []
+
+
+def block_addword():
+    """R += C (one word)."""
+    ins = [("add.cc.u32", "R0", "R0", "C")]
+    for k in range(1, N):
+        ins.append(("addc.cc.u32" if k < N - 1 else "addc.u32", f"R{k}", f"R{k}", "0"))
+    ops = [(f"R{i}", "+r") for i in range(N)] + [("C", "r")]
+    return ops, ins, []
+
+
+def block_sqr_cross_row(i):
+    """(X,Y) += sum_{j>i} a_j * a_i * 2^(32(i+j)) : the cross products of a square, row i (i = 0..6)."""
+    ins, used = [], set()
+    groups = {}
+    for j in range(i + 1, N):
+        pth = i + j
+        arr, lo = ("X", pth) if pth % 2 == 0 else ("Y", pth - 1)
+        groups.setdefault(arr, []).append((j, lo))
+    for arr, lst in groups.items():
+        for k, (j, lo) in enumerate(lst):
+            ins.append(("mad.lo.cc.u32" if k == 0 else "madc.lo.cc.u32", f"{arr}{lo}", f"A{j}", f"A{i}", f"{arr}{lo}"))
+            ins.append(("madc.hi.cc.u32", f"{arr}{lo + 1}", f"A{j}", f"A{i}", f"{arr}{lo + 1}"))
+            used.update((f"{arr}{lo}", f"{arr}{lo + 1}"))
+        nxt = lst[-1][1] + 2
+        if nxt < W:
+            ins.append(("addc.u32", f"{arr}{nxt}", f"{arr}{nxt}", "0"))
+            used.add(f"{arr}{nxt}")
+        else:
+            last = ins.pop()
+            ins.append((last[0].replace(".cc", ""),) + last[1:])
+    names = sorted(used, key=lambda n: (n[0], int(n[1:])))
+    ops = [(n, "+r") for n in names] + [(f"A{j}", "r") for j in range(N)]
+    return ops, ins, []
+
+
+def block_double16(arr):
+    """arr[0..15] *= 2 (no overflow: the doubled cross sum of a square is < 2^512)."""
+    ins = []
+    for k in range(W):
+        op = "add.cc.u32" if k == 0 else ("addc.cc.u32" if k < W - 1 else "addc.u32")
+        ins.append((op, f"{arr}{k}", f"{arr}{k}", f"{arr}{k}"))
+    ops = [(f"{arr}{i}", "+r") for i in range(W)]
+    return ops, ins, []
+
+
+def block_sqr_diag():
+    """X += sum_i a_i^2 * 2^(64 i): the squares sit exactly on the even-aligned pairs."""
+    ins = []
+    for i in range(N):
+        ins.append(("mad.lo.cc.u32" if i == 0 else "madc.lo.cc.u32", f"X{2 * i}", f"A{i}", f"A{i}", f"X{2 * i}"))
+        ins.append(("madc.hi.cc.u32" if i < N - 1 else "madc.hi.u32", f"X{2 * i + 1}", f"A{i}", f"A{i}", f"X{2 * i + 1}"))
+    ops = [(f"X{i}", "+r") for i in range(W)] + [(f"A{j}", "r") for j in range(N)]
+    return ops, ins, []
+
+
 # ----------------------------------------------------------------------------- interpreter
 def run_block(block, env, allow_wrap=False):
     """Execute a block on a dict name->u32. Mirrors PTX semantics of the used subset.
@@ -188,6 +401,8 @@ def run_block(block, env, allow_wrap=False):
             res, cout = ((prod & MASK) if "lo" in parts else (prod >> 32)), cc
         elif base == "and":
             res, cout = srcs[0] & srcs[1], cc
+        elif base == "mov":
+            res, cout = srcs[0], cc
         else:
             raise ValueError(op)
         if sets_cc:
@@ -291,6 +506,55 @@ def generate():
         o.append(f"__device__ __forceinline__ void addp_masked_{name}(uint32_t (&R)[8], uint32_t mk) {{\n")
         o.append(emit_asm(block_addp_masked(p), {**arr("R", "R"), "MK": "mk"}))
         o.append("}\n\n")
+    # ---- wide products / SOS reduction / squaring
+    XY = {**{f"X{i}": f"X[{i}]" for i in range(W)}, **{f"Y{i}": f"Y[{i}]" for i in range(W)}}
+    am16 = {**XY, **arr("a", "A"), "B": "b"}
+    o.append("__device__ __forceinline__ void mulwide_row0(uint32_t (&X)[16], uint32_t (&Y)[16], const uint32_t (&a)[8], uint32_t b) {\n")
+    o.append(emit_asm(block_mulwide_row(0, first=True), am16))
+    o.append("}\n\n")
+    for i in range(1, N):
+        o.append(f"__device__ __forceinline__ void mulwide_row{i}(uint32_t (&X)[16], uint32_t (&Y)[16], const uint32_t (&a)[8], uint32_t b) {{\n")
+        o.append(emit_asm(block_mulwide_row(i), am16))
+        o.append("}\n\n")
+    for i in range(N - 1):
+        o.append(f"__device__ __forceinline__ void sqr_cross_row{i}(uint32_t (&X)[16], uint32_t (&Y)[16], const uint32_t (&a)[8]) {{\n")
+        o.append(emit_asm(block_sqr_cross_row(i), {**XY, **arr("a", "A")}))
+        o.append("}\n\n")
+    o.append("__device__ __forceinline__ void double16(uint32_t (&X)[16]) {\n")
+    o.append(emit_asm(block_double16("X"), XY))
+    o.append("}\n\n")
+    o.append("__device__ __forceinline__ void sqr_diag(uint32_t (&X)[16], const uint32_t (&a)[8]) {\n")
+    o.append(emit_asm(block_sqr_diag(), {**XY, **arr("a", "A")}))
+    o.append("}\n\n")
+    T16 = {f"T{i}": f"T[{i}]" for i in range(W)}
+    o.append("__device__ __forceinline__ void merge16(uint32_t (&T)[16], const uint32_t (&X)[16], const uint32_t (&Y)[16]) {\n  uint32_t co;\n")
+    o.append(emit_asm(block_merge16_lo(), {**T16, **XY, "CO": "co"}))
+    o.append(emit_asm(block_merge16_hi(), {**T16, **XY, "CI": "co"}))
+    o.append("}\n\n")
+    RU = {**arr("R", "R"), **arr("U", "U")}
+    for kind in ("add", "sub"):
+        o.append(f"// T {'+' if kind == 'add' else '-'}= U over 16 limbs (no overflow / no underflow by the caller's bounds)\n")
+        o.append(f"__device__ __forceinline__ void {kind}16(uint32_t (&T)[16], const uint32_t (&U)[16]) {{\n  uint32_t co;\n")
+        lo = {**{f"R{i}": f"T[{i}]" for i in range(8)}, **{f"U{i}": f"U[{i}]" for i in range(8)}, "CO": "co"}
+        hi = {**{f"R{i}": f"T[{8 + i}]" for i in range(8)}, **{f"U{i}": f"U[{8 + i}]" for i in range(8)}, "CI": "co"}
+        o.append(emit_asm(block_addsub8(kind, False, True), lo))
+        o.append(emit_asm(block_addsub8(kind, True, False), hi))
+        o.append("}\n\n")
+    for name, p in FIELDS.items():
+        for i in range(N):
+            o.append(f"__device__ __forceinline__ void redc16_step{i}_{name}(uint32_t (&X)[16], uint32_t (&Y)[16], uint32_t (&K)[8], uint32_t& c) {{\n")
+            o.append(emit_asm(block_redc16_step(i, p), {**XY, **{f"K{j}": f"K[{j}]" for j in range(8)}, "C": "c"}))
+            o.append("}\n\n")
+        p2 = p * p
+        o.append(f"// T += p^2 (16 limbs)\n__device__ __forceinline__ void addp2_{name}(uint32_t (&T)[16]) {{\n  uint32_t co;\n")
+        o.append(emit_asm(block_addconst8(p2 & ((1 << 256) - 1), False, True), {**{f"R{i}": f"T[{i}]" for i in range(8)}, "CO": "co"}))
+        o.append(emit_asm(block_addconst8(p2 >> 256, True, False), {**{f"R{i}": f"T[{8 + i}]" for i in range(8)}, "CI": "co"}))
+        o.append("}\n\n")
+    o.append("__device__ __forceinline__ void redc16_final(uint32_t (&R)[8], const uint32_t (&X)[16], const uint32_t (&Y)[16], const uint32_t (&K)[8], uint32_t c) {\n")
+    o.append(emit_asm(block_redc16_final(), {**arr("R", "R"), **XY}))
+    o.append(emit_asm(block_addk(), {**arr("R", "R"), **{f"K{j}": f"K[{j}]" for j in range(8)}}))
+    o.append(emit_asm(block_addword(), {**arr("R", "R"), "C": "c"}))
+    o.append("}\n\n")
     o.append("#endif // __CUDA_ARCH__\n\n}} // namespace b200::ptx\n")
     return "".join(o)
 
