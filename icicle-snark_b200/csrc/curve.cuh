@@ -105,7 +105,7 @@ namespace b200 {
       F ppp = pp_ * pp;
       F q = x * pp;
       F x3 = r.sqr() - ppp - q.dbl();
-      y = r * (q - x3) - y * ppp;
+      y = F::mul_sub(r, q - x3, y, ppp);
       x = x3;
       zz = zz * pp;
       zzz = zzz * ppp;
@@ -136,7 +136,7 @@ namespace b200 {
       F ppp = pp_ * pp;
       F q = u1 * pp;
       F x3 = r.sqr() - ppp - q.dbl();
-      y = r * (q - x3) - s1 * ppp;
+      y = F::mul_sub(r, q - x3, s1, ppp);
       x = x3;
       zz = zz * o.zz * pp;
       zzz = zzz * o.zzz * ppp;
