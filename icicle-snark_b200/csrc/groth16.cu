@@ -229,7 +229,7 @@ namespace b200 {
   {
     if (!zkey || !out) return ICICLE_INVALID_POINTER;
     if (world < 1 || rank < 0 || rank >= world) return ICICLE_INVALID_ARGUMENT;
-    B200_TRY(ensure_device());
+    // (format validation first: malformed input is INVALID_ARGUMENT on any machine, with or without a GPU)
     std::map<uint32_t, Section> sec;
     if (!parse_binfile(zkey, zkey_len, "zkey", 2, sec)) return ICICLE_INVALID_ARGUMENT;
     for (uint32_t id : {1u, 2u, 4u, 5u, 6u, 7u, 8u, 9u})
@@ -249,6 +249,15 @@ namespace b200 {
     if (n8q != 32 || memcmp(p + 4, FQ_MODULUS, 32) != 0) return ICICLE_INVALID_ARGUMENT; // not BN254
     memcpy(&n8r, p + 36, 4);
     if (n8r != 32 || memcmp(p + 40, FR_MODULUS, 32) != 0) return ICICLE_INVALID_ARGUMENT;
+    {
+      // header sanity before touching the device
+      uint32_t nv, npub, dom;
+      memcpy(&nv, p + 72, 4);
+      memcpy(&npub, p + 76, 4);
+      memcpy(&dom, p + 80, 4);
+      if (dom == 0 || (dom & (dom - 1)) || nv == 0 || npub + 1 > nv) return ICICLE_INVALID_ARGUMENT;
+    }
+    B200_TRY(ensure_device());
     b200_zkey_cache* c = new b200_zkey_cache();
     c->device = active_device();
     c->rank = rank;
@@ -836,6 +845,16 @@ eIcicleError b200_groth16_prove(
   compute_blind(cache, r, s, bt); // host work overlapped with the GPU
   B200_TRY(commit_wait(cache, &parts, tm));
   return finish_with(cache, &parts, 1, bt, proof);
+}
+
+// proof.json text for a proof struct (what b200_groth16_prove_files writes); returns the length, or 0 if cap is too small
+size_t b200_proof_to_json(const b200_groth16_proof* proof, char* out, size_t cap)
+{
+  if (!proof || !out) return 0;
+  std::string s = proof_json(*proof);
+  if (s.size() + 1 > cap) return 0;
+  memcpy(out, s.c_str(), s.size() + 1);
+  return s.size();
 }
 
 eIcicleError b200_groth16_prove_files(

@@ -297,6 +297,10 @@ eIcicleError b200_groth16_finish(const b200_zkey_cache* cache, const b200_groth1
 eIcicleError b200_groth16_prove_files(const char* witness_path, const char* zkey_path, const char* proof_path,
                                       const char* public_path, const char* device);
 
+/* The proof.json text b200_groth16_prove_files writes for `proof` (serde_json pretty layout, src/proof_helper.rs:308-316);
+ * returns its length, 0 if `cap` is too small. Host-only. */
+size_t b200_proof_to_json(const b200_groth16_proof* proof, char* out, size_t cap);
+
 /* Synthetic-setup / test tool: out[i] = k_i * G1 (64 B affine) or k_i * G2 (128 B affine),
  * k in standard form, host or icicle_malloc'd memory; output Montgomery (as .zkey stores) or standard form.
  * The reference generates its benchmark zkeys with snarkjs (scripts/setup.sh), which is unavailable offline. */
