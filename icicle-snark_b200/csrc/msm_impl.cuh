@@ -431,6 +431,7 @@ namespace b200 {
       cudaStreamSynchronize(st); // `id` is a stack temporary
     } else {
       MsmPlan plan = make_msm_plan(msm_size, cfg->c, bitsize, f, g2);
+      if (plan.entries() >= (1ull << 32)) err = ICICLE_INVALID_ARGUMENT; // entry positions are 32-bit
       for (int b = 0; b < batch && err == ICICLE_SUCCESS; ++b) {
         err = msm_enqueue<F>(
           plan, (const Fr*)S.dev + (size_t)b * msm_size, cfg->are_scalars_montgomery_form,
