@@ -262,6 +262,16 @@ namespace b200 {
     c->device = active_device();
     c->rank = rank;
     c->world = world;
+    if (precompute == 0) {
+      // auto: keep the 2^(c*j) multiples of every base point resident when they fit comfortably (a third of the free
+      // HBM); at 3200k that is 17.8 GB of 180 and takes the proof from ~72 ms to ~59 ms
+      uint32_t nv, dom;
+      memcpy(&nv, h.p + 72, 4);
+      memcpy(&dom, h.p + 80, 4);
+      size_t free_b = 0, total_b = 0;
+      const size_t tables = ((size_t)nv * (3 * 64 + 128) + (size_t)dom * 64) * 16 / (size_t)world;
+      precompute = (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && tables < free_b / 3) ? 16 : 1;
+    }
     c->precompute = precompute > 1 ? precompute : 1;
     memcpy(&c->n_vars, p + 72, 4);
     memcpy(&c->n_public, p + 76, 4);
@@ -877,7 +887,7 @@ eIcicleError b200_groth16_prove_files(
       MappedFile zk;
       if (!zk.open(zkey_path)) return ICICLE_INVALID_ARGUMENT;
       const char* pf = getenv("B200_PRECOMPUTE");
-      B200_TRY(cache_build(zk.p, zk.len, pf ? atoi(pf) : 1, 0, 1, &cache));
+      B200_TRY(cache_build(zk.p, zk.len, pf ? atoi(pf) : 0 /* auto */, 0, 1, &cache));
       g_cache_manager[key] = cache;
     } else {
       cache = it->second;

@@ -251,7 +251,8 @@ typedef struct {              /* per-phase device times of the last prove, milli
 } b200_prove_timings;
 
 /* Build the cache from an in-memory .zkey image (the mmap the reference takes in cache.rs:117-181).
- * `precompute` > 1 stores 2^(c*j)-multiples of every base so all MSM windows share one bucket set. */
+ * `precompute` > 1 stores 2^(c*j)-multiples of every base so all MSM windows share one bucket set;
+ * 0 = choose automatically (16 when the tables fit in a third of the free device memory, else 1). */
 eIcicleError b200_zkey_cache_create(const uint8_t* zkey, size_t zkey_len, int precompute, b200_zkey_cache** out);
 eIcicleError b200_zkey_cache_destroy(b200_zkey_cache* cache);
 eIcicleError b200_zkey_cache_info(const b200_zkey_cache* cache, uint32_t* n_vars, uint32_t* n_public,
