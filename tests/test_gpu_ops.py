@@ -329,3 +329,44 @@ def test_ntt_errors_are_codes_not_exceptions(gpu, rng, domains):
     big = np.zeros((1 << 21, 8), dtype=np.uint32)
     with pytest.raises(B.IcicleError):
         gpu.ntt(big, B.kForward)  # larger than the domain (the reference throws across the ABI here)
+
+
+def test_ntt_full_size_properties(gpu, rng):
+    """BASELINE size (2^22, batch 3, in place on the device): iNTT(NTT(x)) == x and linearity NTT(x + y) == NTT(x) + NTT(y)
+    - size-independent properties where the CPU reference would take tens of seconds."""
+    import torch
+    logn, batch = 22, 3
+    n = 1 << logn
+    gpu.ntt_release_domain()
+    gpu.ntt_init_domain(gpu.get_root_of_unity(n))
+    try:
+        def rnd():
+            t = torch.randint(0, 1 << 31, (n * batch, 8), dtype=torch.int32, device="cuda")
+            t[:, 7] &= 0x0FFFFFFF  # < r
+            return t
+        x, y = rnd(), rnd()
+        cfg = B.NTTConfig.default()
+        cfg.batch_size = batch
+        cfg.are_inputs_on_device = cfg.are_outputs_on_device = True
+        vcfg = B.VecOpsConfig.default()
+        vcfg.is_a_on_device = vcfg.is_b_on_device = vcfg.is_result_on_device = True
+
+        def vadd(a, b):
+            o = torch.empty_like(a)
+            B.check(gpu.dll.bn254_vector_add(C.c_void_p(a.data_ptr()), C.c_void_p(b.data_ptr()), C.c_uint64(n * batch), C.byref(vcfg),
+                                             C.c_void_p(o.data_ptr())))
+            return o
+
+        def ntt(a, d, inplace=False):
+            o = a if inplace else torch.empty_like(a)
+            gpu.ntt(a.data_ptr(), d, cfg, out=o.data_ptr(), size=n)
+            return o
+
+        fx, fy = ntt(x, B.kForward), ntt(y, B.kForward)
+        fxy = ntt(vadd(x, y), B.kForward)
+        assert torch.equal(fxy, vadd(fx, fy))
+        back = ntt(fx.clone(), B.kInverse, inplace=True)
+        assert torch.equal(back, x)
+        assert not torch.equal(fx, x)
+    finally:
+        gpu.ntt_release_domain()
