@@ -114,6 +114,13 @@ namespace b200 {
     }
   }
 
+  // wb[k] = w[idx[k]]: witness values of the signals that have a B point
+  static __global__ void __launch_bounds__(256) gather_scalars_kernel(const Fr* w, const uint32_t* idx, uint32_t n, Fr* out)
+  {
+    for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x)
+      st_fr(out + k, ld_fr(w + idx[k]));
+  }
+
   struct PowTab {
     Fr pw[30];
   };
@@ -148,6 +155,12 @@ struct b200_zkey_cache {
   G1Affine *pA = nullptr, *pB1 = nullptr, *pC = nullptr, *pH = nullptr;
   G2Affine* pB2 = nullptr;
   MsmPlan planA, planC, planH, planB2;
+  // B1/B2 columns that are points at infinity (signals absent from every B row: the norm in circom circuits) are
+  // dropped at build time when they are >= 1/8 of the shard: idxB lists the surviving signals (relative to a_lo)
+  uint32_t* idxB = nullptr;
+  uint32_t n_b = 0;   // number of B points kept (== a_hi - a_lo when dense)
+  bool b_sparse = false;
+  Fr* d_wb = nullptr; // gathered witness values for the sparse B MSMs
   // R1CS in CSR over rows [A rows 0..N) | B rows 0..N)]
   uint32_t *row_ptr = nullptr, *col = nullptr;
   Fr* val = nullptr;
@@ -155,6 +168,7 @@ struct b200_zkey_cache {
   // per-proof workspace
   Fr *d_witness = nullptr, *d_vec = nullptr, *d_h = nullptr;
   uint8_t* d_results = nullptr; // 4 x G1 projective + 1 x G2 projective
+  uint8_t* d_scratch_results = nullptr; // 2 x G1 projective (A, C of the sparse-B path)
   uint8_t* h_results = nullptr; // pinned
   cudaStream_t s_copy = nullptr, s_g1 = nullptr, s_g2 = nullptr, s_q = nullptr;
   cudaEvent_t ev_wit = nullptr, ev_start = nullptr, ev_h2d = nullptr, ev_r1cs = nullptr, ev_ntt = nullptr, ev_g1 = nullptr,
@@ -184,7 +198,7 @@ namespace b200 {
     if (!c) return;
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
-    void* ptrs[] = {c->pA, c->pB1, c->pC, c->pH, c->pB2, c->row_ptr, c->col, c->val, c->keys, c->d_witness, c->d_vec, c->d_h, c->d_results};
+    void* ptrs[] = {c->idxB, c->d_wb, c->pA, c->pB1, c->pC, c->pH, c->pB2, c->row_ptr, c->col, c->val, c->keys, c->d_witness, c->d_vec, c->d_h, c->d_results, c->d_scratch_results};
     for (void* p : ptrs)
       if (p) cudaFree(p);
     if (c->h_results) cudaFreeHost(c->h_results);
@@ -200,6 +214,32 @@ namespace b200 {
   // Upload the [lo,hi) slice of the logical array  zeros(prefix) ++ section  (prefix points at infinity in front let
   // the C section, which starts at signal n_public+1, share the witness indexing of A/B1/B2); with precompute > 1
   // expand it into the [i*f + j] = 2^(shift*j) P_i table the MSM consumes (cuda_msm.cuh:29-43 layout)
+  // Upload only the listed points (keep[k] = index relative to lo) of a section: the compacted B1/B2 tables
+  template <class F>
+  static eIcicleError upload_points_compact(
+    b200_zkey_cache* c, const Section& sec, uint32_t lo, const std::vector<uint32_t>& keep, const MsmPlan& plan, Affine<F>** out,
+    cudaStream_t st)
+  {
+    const size_t n = keep.size();
+    const int f = plan.factor;
+    B200_CUDA(dev_alloc(out, n * f, c), ICICLE_ALLOCATION_FAILED);
+    if (n == 0) return ICICLE_SUCCESS;
+    std::vector<Affine<F>> host(n);
+    const Affine<F>* src = reinterpret_cast<const Affine<F>*>(sec.p) + lo;
+    for (size_t k = 0; k < n; ++k)
+      memcpy(&host[k], src + keep[k], sizeof(Affine<F>));
+    Affine<F>* tmp = *out;
+    if (f > 1) B200_CUDA(cudaMallocAsync((void**)&tmp, n * sizeof(Affine<F>), st), ICICLE_ALLOCATION_FAILED);
+    B200_CUDA(cudaMemcpyAsync(tmp, host.data(), n * sizeof(Affine<F>), cudaMemcpyHostToDevice, st), ICICLE_COPY_FAILED);
+    eIcicleError e = ICICLE_SUCCESS;
+    if (f > 1) {
+      e = precompute_enqueue<F>(tmp, true, (int)n, f, plan.c * plan.sets, *out, true, st);
+      cudaFreeAsync(tmp, st);
+    }
+    B200_CUDA(cudaStreamSynchronize(st), ICICLE_SYNCHRONIZATION_FAILED); // `host` goes out of scope
+    return e;
+  }
+
   template <class F>
   static eIcicleError upload_points(
     b200_zkey_cache* c, const Section& sec, uint32_t prefix, uint32_t lo, uint32_t hi, const MsmPlan& plan, Affine<F>** out,
@@ -348,8 +388,38 @@ namespace b200 {
     c->planB2 = c->planA; // same digits/windows as the G1 MSMs: B2 reuses their sort
     c->planH = plan_for(c->h_hi - c->h_lo, false);
     if ((err = upload_points<Fq>(c, sec[5], 0, c->a_lo, c->a_hi, c->planA, &c->pA, st)) != ICICLE_SUCCESS) return fail(err);
-    if ((err = upload_points<Fq>(c, sec[6], 0, c->a_lo, c->a_hi, c->planA, &c->pB1, st)) != ICICLE_SUCCESS) return fail(err);
-    if ((err = upload_points<Fq2>(c, sec[7], 0, c->a_lo, c->a_hi, c->planB2, &c->pB2, st)) != ICICLE_SUCCESS) return fail(err);
+    {
+      // which signals of the shard have a B point at all? (B1 and B2 are zero together: same v_s(tau))
+      const uint32_t n_sh = c->a_hi - c->a_lo;
+      std::vector<uint32_t> keep;
+      keep.reserve(n_sh);
+      const uint64_t* b1 = reinterpret_cast<const uint64_t*>(sec[6].p) + (size_t)c->a_lo * 8;
+      const uint64_t* b2 = reinterpret_cast<const uint64_t*>(sec[7].p) + (size_t)c->a_lo * 16;
+      for (uint32_t i = 0; i < n_sh; ++i) {
+        uint64_t any = 0;
+        for (int k = 0; k < 8; ++k)
+          any |= b1[(size_t)i * 8 + k];
+        for (int k = 0; k < 16; ++k)
+          any |= b2[(size_t)i * 16 + k];
+        if (any) keep.push_back(i);
+      }
+      const char* sp = getenv("B200_SPARSE_B"); // 0 = never compact, 1 = always (tests), default: >= 1/8 at infinity
+      const bool want = sp ? sp[0] == '1' : (n_sh - keep.size()) * 8 >= (size_t)n_sh;
+      if (want && n_sh > 0) {
+        c->b_sparse = true;
+        c->n_b = (uint32_t)keep.size();
+        c->planB2 = plan_for(c->n_b, false);
+        CK(dev_alloc(&c->idxB, keep.size(), c));
+        CK(dev_alloc(&c->d_wb, keep.size(), c));
+        CK(cudaMemcpyAsync(c->idxB, keep.data(), keep.size() * 4, cudaMemcpyHostToDevice, st));
+        if ((err = upload_points_compact<Fq>(c, sec[6], c->a_lo, keep, c->planB2, &c->pB1, st)) != ICICLE_SUCCESS) return fail(err);
+        if ((err = upload_points_compact<Fq2>(c, sec[7], c->a_lo, keep, c->planB2, &c->pB2, st)) != ICICLE_SUCCESS) return fail(err);
+      } else {
+        c->n_b = n_sh;
+        if ((err = upload_points<Fq>(c, sec[6], 0, c->a_lo, c->a_hi, c->planA, &c->pB1, st)) != ICICLE_SUCCESS) return fail(err);
+        if ((err = upload_points<Fq2>(c, sec[7], 0, c->a_lo, c->a_hi, c->planB2, &c->pB2, st)) != ICICLE_SUCCESS) return fail(err);
+      }
+    }
     if ((err = upload_points<Fq>(c, sec[8], c->n_public + 1, c->c_lo, c->c_hi, c->planC, &c->pC, st)) != ICICLE_SUCCESS)
       return fail(err);
     if ((err = upload_points<Fq>(c, sec[9], 0, c->h_lo, c->h_hi, c->planH, &c->pH, st)) != ICICLE_SUCCESS) return fail(err);
@@ -419,6 +489,7 @@ namespace b200 {
     CK(dev_alloc(&c->d_vec, 3 * (size_t)N, c));
     CK(dev_alloc(&c->d_h, (size_t)N, c));
     CK(dev_alloc(&c->d_results, (size_t)4 * 96 + 192, c));
+    CK(dev_alloc(&c->d_scratch_results, (size_t)2 * 96, c));
     CK(cudaHostAlloc((void**)&c->h_results, 4 * 96 + 192, cudaHostAllocDefault));
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(st)); // host vectors go out of scope
@@ -498,7 +569,34 @@ namespace b200 {
   {
     ResultSlots r = result_slots(c);
     const Fr* w = c->d_witness;
-    if (c->a_hi > c->a_lo) {
+    if (c->a_hi > c->a_lo && c->b_sparse) {
+      // sparse B: A and C share the signal-indexed sort (s_g1); B1 and B2 share a second, shorter sort over the
+      // gathered witness values of the signals that have a B point (s_g2)
+      MsmSorted sorted_ac, sorted_b;
+      B200_TRY(msm_sort_enqueue(c->planA, w + c->a_lo, false, &sorted_ac, c->s_g1));
+      const G1Affine* ac_tables[2] = {c->pA, c->pC};
+      G1Projective* tmp_ac = (G1Projective*)c->d_scratch_results; // A, C contiguous
+      B200_TRY(msm_reduce_enqueue<Fq>(c->planA, sorted_ac, ac_tables, 2, tmp_ac, c->s_g1));
+      cudaMemcpyAsync(r.a, tmp_ac, 96, cudaMemcpyDeviceToDevice, c->s_g1);
+      cudaMemcpyAsync(r.c, tmp_ac + 1, 96, cudaMemcpyDeviceToDevice, c->s_g1);
+      msm_sorted_free(&sorted_ac, c->s_g1);
+      if (c->n_b > 0) {
+        B200_LAUNCH(gather_scalars_kernel, grid_for(c->n_b, 256, 8), 256, 0, c->s_g2, w + c->a_lo, c->idxB, c->n_b, c->d_wb);
+        B200_TRY(msm_sort_enqueue(c->planB2, c->d_wb, false, &sorted_b, c->s_g2));
+        const G1Affine* b1_tables[1] = {c->pB1};
+        const G2Affine* b2_tables[1] = {c->pB2};
+        B200_TRY(msm_reduce_enqueue<Fq2>(c->planB2, sorted_b, b2_tables, 1, r.b2, c->s_g2));
+        B200_TRY(msm_reduce_enqueue<Fq>(c->planB2, sorted_b, b1_tables, 1, r.b1, c->s_g2));
+        msm_sorted_free(&sorted_b, c->s_g2);
+      } else {
+        // no signal has a B point: both commitments are the identity
+        static const G1Projective id1 = {Fq::zero(), Fq::raw_one(), Fq::zero()};
+        static const G2Projective id2 = {Fq2::zero(), {Fq::raw_one(), Fq::zero()}, Fq2::zero()};
+        cudaMemcpyAsync(r.b1, &id1, 96, cudaMemcpyHostToDevice, c->s_g2);
+        cudaMemcpyAsync(r.b2, &id2, 192, cudaMemcpyHostToDevice, c->s_g2);
+      }
+      cudaEventRecord(c->ev_g2, c->s_g2);
+    } else if (c->a_hi > c->a_lo) {
       MsmSorted sorted;
       B200_TRY(msm_sort_enqueue(c->planA, w + c->a_lo, false, &sorted, c->s_g1));
       cudaEventRecord(c->ev_b1, c->s_g1); // sort done
@@ -822,6 +920,14 @@ eIcicleError b200_groth16_commit_end(
   if (e == ICICLE_SUCCESS) e = commit_wait(c, out, tm);
   c->mu.unlock();
   return e;
+}
+
+eIcicleError b200_zkey_cache_b_points(const b200_zkey_cache* c, uint32_t* kept, uint32_t* total)
+{
+  if (!c || !kept || !total) return ICICLE_INVALID_POINTER;
+  *kept = c->n_b;
+  *total = c->a_hi - c->a_lo;
+  return ICICLE_SUCCESS;
 }
 
 eIcicleError b200_zkey_cache_h_range(const b200_zkey_cache* c, uint32_t* lo, uint32_t* hi)

@@ -72,6 +72,11 @@ class ZKeyCache:
         check(self.lib.dll.b200_zkey_cache_h_range(self.handle, C.byref(lo), C.byref(hi)))
         return lo.value, hi.value
 
+    def b_points(self):
+        kept, total = C.c_uint32(), C.c_uint32()
+        check(self.lib.dll.b200_zkey_cache_b_points(self.handle, C.byref(kept), C.byref(total)))
+        return kept.value, total.value
+
     def commit_begin(self, witness, first_poly, poly_count, out_dev_ptr, n_witness=None):
         """N > 1 quotient split, phase 1 (see include/icicle_b200.h)."""
         wp, n = self._wptr(witness, n_witness)

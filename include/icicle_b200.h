@@ -289,6 +289,9 @@ eIcicleError b200_groth16_commit_begin(b200_zkey_cache* cache, const bn254_scala
 eIcicleError b200_groth16_commit_end(b200_zkey_cache* cache, const void* a_dev, const void* b_dev, const void* c_dev,
                                      b200_groth16_partials* out, b200_prove_timings* timings);
 eIcicleError b200_zkey_cache_h_range(const b200_zkey_cache* cache, uint32_t* lo, uint32_t* hi);
+/* B1/B2 points kept in this rank's shard after dropping the columns at infinity (signals absent from every B row; dropped
+ * when they are >= 1/8 of the shard, B200_SPARSE_B=0/1 overrides) and the shard's signal count. */
+eIcicleError b200_zkey_cache_b_points(const b200_zkey_cache* cache, uint32_t* kept, uint32_t* total);
 eIcicleError b200_groth16_finish(const b200_zkey_cache* cache, const b200_groth16_partials* parts, int n_parts,
                                  const bn254_scalar_t* r, const bn254_scalar_t* s, b200_groth16_proof* proof);
 

@@ -186,3 +186,32 @@ def test_quotient_split_api_single_rank(gpu):
         assert pkg.proof_json(p2) == gold11
     finally:
         cache.close()
+
+
+def test_sparse_b_columns_are_dropped_and_proofs_unchanged(gpu, ref, monkeypatch):
+    """Signals absent from every B row have B1/B2 points at infinity; the cache drops them (second, shorter sort for
+    B1/B2). Forced on a dense golden instance, natural on the random circuit; proofs must not change."""
+    zkey, wtns, vk, gold11, goldrs, _ = load(100)
+    w = wtns_words(wtns)
+    monkeypatch.setenv("B200_SPARSE_B", "1")
+    for precompute, world in ((1, 1), (16, 1), (1, 3)):
+        caches = [pkg.ZKeyCache(gpu, zkey, precompute=precompute, rank=r, world=world) for r in range(world)]
+        try:
+            kept = sum(c.b_points()[0] for c in caches)
+            assert kept == 100  # signals 0 and 1 (one, c) never appear in B
+            parts = [c.commit_partials(w)[0] for c in caches]
+            assert pkg.proof_json(caches[0].finish(parts, FIXED_R, FIXED_S)) == goldrs
+        finally:
+            for c in caches:
+                c.close()
+    monkeypatch.delenv("B200_SPARSE_B")
+    zkey, wtns, vk = synth.make_random_circuit(gpu, 6000, n_inputs=200, n_public=9, seed=b"sparse", rng_seed=11)
+    proof_ref, public = G.prove(ref, pkg.bindings, zkey, wtns, FIXED_R, FIXED_S)
+    cache = pkg.ZKeyCache(gpu, zkey, precompute=16)
+    try:
+        kept, total = cache.b_points()
+        assert kept < total * 7 // 8  # the heuristic switched the sparse path on by itself
+        p, _ = cache.prove(wtns_words(wtns), FIXED_R, FIXED_S)
+        assert pkg.proof_json(p) == G.proof_json(proof_ref)
+    finally:
+        cache.close()
