@@ -16,9 +16,11 @@
 //     crosses PCIe twice and scatters in a single-thread loop, proof_helper.rs:55-99).
 //   * iNTT -> x keys -> NTT runs on the Stockham passes of ntt.cu with 1/N * keys fused into the last
 //     iNTT pass; A'.B' - C' and the conversion to standard form are one kernel.
-//   * A, B1, C, B2 start as soon as the witness is on the device, each on its own stream, concurrently with the
-//     quotient chain; H follows on the chain's (higher-priority) stream.  No host synchronisation until the
-//     five results are back.
+//   * A, B1, C, B2 take the same scalars: one digit decomposition + counting sort feeds ONE three-table G1 launch
+//     (s_g1) and the G2 launch (s_g2); they start as soon as the witness is on the device, concurrently with the
+//     quotient chain, and H follows on the chain's (higher-priority) stream.  B columns at infinity are dropped at
+//     build time (sparse-B path).  No host synchronisation until the five results are back; the blinding multiples
+//     of delta are computed on the host meanwhile.
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
@@ -171,8 +173,8 @@ struct b200_zkey_cache {
   uint8_t* d_scratch_results = nullptr; // 2 x G1 projective (A, C of the sparse-B path)
   uint8_t* h_results = nullptr; // pinned
   cudaStream_t s_copy = nullptr, s_g1 = nullptr, s_g2 = nullptr, s_q = nullptr;
-  cudaEvent_t ev_wit = nullptr, ev_start = nullptr, ev_h2d = nullptr, ev_r1cs = nullptr, ev_ntt = nullptr, ev_g1 = nullptr,
-              ev_g2 = nullptr, ev_q = nullptr, ev_prev = nullptr, ev_b1 = nullptr, ev_c = nullptr;
+  cudaEvent_t ev_start = nullptr, ev_h2d = nullptr, ev_r1cs = nullptr, ev_ntt = nullptr, ev_g1 = nullptr,
+              ev_g2 = nullptr, ev_q = nullptr, ev_prev = nullptr, ev_b1 = nullptr;
   std::mutex mu;
 };
 
@@ -205,7 +207,7 @@ namespace b200 {
     cudaStream_t ss[] = {c->s_copy, c->s_g1, c->s_g2, c->s_q};
     for (auto s : ss)
       if (s) cudaStreamDestroy(s);
-    cudaEvent_t es[] = {c->ev_wit, c->ev_start, c->ev_h2d, c->ev_r1cs, c->ev_ntt, c->ev_g1, c->ev_g2, c->ev_q, c->ev_prev, c->ev_b1, c->ev_c};
+    cudaEvent_t es[] = {c->ev_start, c->ev_h2d, c->ev_r1cs, c->ev_ntt, c->ev_g1, c->ev_g2, c->ev_q, c->ev_prev, c->ev_b1};
     for (auto e : es)
       if (e) cudaEventDestroy(e);
     delete c;
@@ -367,7 +369,7 @@ namespace b200 {
     CK(cudaStreamCreateWithPriority(&c->s_q, cudaStreamNonBlocking, use_prio ? prio_hi : prio_lo));
     CK(cudaStreamCreateWithPriority(&c->s_g2, cudaStreamNonBlocking, use_prio && prio_hi + 1 <= prio_lo ? prio_hi + 1 : prio_lo));
     CK(cudaStreamCreateWithPriority(&c->s_g1, cudaStreamNonBlocking, prio_lo));
-    for (cudaEvent_t* e : {&c->ev_wit, &c->ev_prev, &c->ev_b1, &c->ev_c})
+    for (cudaEvent_t* e : {&c->ev_prev, &c->ev_b1})
       CK(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
     for (cudaEvent_t* e : {&c->ev_start, &c->ev_h2d, &c->ev_r1cs, &c->ev_ntt, &c->ev_g1, &c->ev_g2, &c->ev_q})
       CK(cudaEventCreate(e));
