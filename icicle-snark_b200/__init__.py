@@ -5,6 +5,7 @@ Rust toolchain; see INTEGRATION.md for the Rust-side binding):
 
   bindings.IcicleLib   <-> wrappers/rust/icicle-{runtime,core,curves/icicle-bn254}  (op-level C ABI)
   prover.groth16_prove <-> src/lib.rs:33-61, src/cache.rs CacheManager               (fused C ABI)
+  prover.groth16_verify <-> src/lib.rs:63-82, src/proof_helper.rs:319-372            (host pairing, as in the reference)
 
 All arithmetic is in csrc/ (hand-written sm_100a CUDA behind lib/libicicle_b200.so).  There is no
 CPU fallback: loading fails loudly if the library has not been built.
@@ -39,5 +40,6 @@ def lib() -> IcicleLib:
         _lib = IcicleLib(LIB_PATH)
     return _lib
 
-from .prover import CacheManager, ZKeyCache, groth16_prove, proof_json, proof_to_dict  # noqa: E402,F401
+from .prover import (CacheManager, ZKeyCache, groth16_prove, groth16_verify, groth16_verify_points,  # noqa: E402,F401
+                     proof_json, proof_to_dict)
 from . import multi_gpu  # noqa: E402,F401

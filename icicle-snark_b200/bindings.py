@@ -23,6 +23,7 @@ import numpy as np
 SCALAR_WORDS = 8
 G1_AFFINE_WORDS, G1_PROJ_WORDS = 16, 24
 G2_AFFINE_WORDS, G2_PROJ_WORDS = 32, 48
+FQ12_WORDS = 96
 
 ERRORS = [
     "SUCCESS", "INVALID_DEVICE", "OUT_OF_MEMORY", "INVALID_POINTER", "ALLOCATION_FAILED",
@@ -140,6 +141,9 @@ bn254_generate_projective_points bn254_generate_affine_points
 bn254_g2_eq bn254_g2_is_on_curve bn254_g2_to_affine bn254_g2_from_affine bn254_g2_generator bn254_g2_ecadd
 bn254_g2_ecsub bn254_g2_mul_scalar bn254_g2_generate_projective_points bn254_g2_generate_affine_points
 bn254_g2_base_field_from_u32
+bn254_pairing bn254_pairing_target_field_generate_scalars bn254_pairing_target_field_add bn254_pairing_target_field_sub
+bn254_pairing_target_field_mul bn254_pairing_target_field_inv bn254_pairing_target_field_pow
+bn254_pairing_target_field_from_u32
 """.split()
 
 # the fused fast path: only libicicle_b200 has these
@@ -148,6 +152,7 @@ b200_zkey_cache_create b200_zkey_cache_destroy b200_zkey_cache_info b200_groth16
 b200_zkey_cache_create_sharded b200_groth16_commit_partials b200_groth16_finish b200_groth16_prove_files
 b200_groth16_commit_begin b200_groth16_commit_end b200_zkey_cache_h_range b200_proof_to_json b200_zkey_cache_b_points
 b200_version b200_launch_count b200_imad_peak b200_pipe_peak b200_fixed_base_mul b200_profile_accumulate
+b200_groth16_verify b200_groth16_verify_files
 """.split()
 
 
@@ -420,6 +425,49 @@ class IcicleLib:
     def ecsub(self, a, b, g2=False):
         o = np.zeros_like(a)
         getattr(self.dll, self._pfx(g2) + "ecsub")(_ptr(np.ascontiguousarray(a)), _ptr(np.ascontiguousarray(b)), _ptr(o))
+        return o
+
+    # ---- pairing (rust icicle-core/src/pairing/mod.rs: pairing(), PairingTargetField) ----------------
+    def pairing(self, p_affine, q_affine):
+        """e(P, Q) as 96 words (Fq12, standard form); host code in the reference too (icicle/src/pairing.cpp:20-24)"""
+        o = np.zeros(FQ12_WORDS, dtype=np.uint32)
+        self.dll.bn254_pairing(_ptr(np.ascontiguousarray(p_affine, dtype=np.uint32)),
+                               _ptr(np.ascontiguousarray(q_affine, dtype=np.uint32)), _ptr(o))
+        return o
+
+    def _t3(self, name, a, b):
+        o = np.zeros(FQ12_WORDS, dtype=np.uint32)
+        getattr(self.dll, name)(_ptr(np.ascontiguousarray(a, dtype=np.uint32)),
+                                _ptr(np.ascontiguousarray(b, dtype=np.uint32)), _ptr(o))
+        return o
+
+    def target_add(self, a, b):
+        return self._t3("bn254_pairing_target_field_add", a, b)
+
+    def target_sub(self, a, b):
+        return self._t3("bn254_pairing_target_field_sub", a, b)
+
+    def target_mul(self, a, b):
+        return self._t3("bn254_pairing_target_field_mul", a, b)
+
+    def target_inv(self, a):
+        o = np.zeros(FQ12_WORDS, dtype=np.uint32)
+        self.dll.bn254_pairing_target_field_inv(_ptr(np.ascontiguousarray(a, dtype=np.uint32)), _ptr(o))
+        return o
+
+    def target_pow(self, a, e):
+        o = np.zeros(FQ12_WORDS, dtype=np.uint32)
+        self.dll.bn254_pairing_target_field_pow(_ptr(np.ascontiguousarray(a, dtype=np.uint32)), C.c_int(e), _ptr(o))
+        return o
+
+    def target_from_u32(self, v):
+        o = np.zeros(FQ12_WORDS, dtype=np.uint32)
+        self.dll.bn254_pairing_target_field_from_u32(C.c_uint32(v), _ptr(o))
+        return o
+
+    def target_generate(self, n):
+        o = words(n, FQ12_WORDS)
+        self.dll.bn254_pairing_target_field_generate_scalars(_ptr(o), C.c_int(n))
         return o
 
     def mul_scalar(self, p, s, g2=False):

@@ -2,8 +2,8 @@
 // Same line protocol, defaults and sentinels: "prove --witness P --zkey P --proof P --public P --device CUDA",
 // "exit"; prints COMMAND_EMPTY / COMMAND_EXIT / COMMAND_COMPLETED.  One process-wide cache (the CacheManager
 // lives inside the library, keyed "{zkey}_{device}"), so the second proof for a zkey is warm.
-// `verify` is the reference's CPU-only pairing path (src/proof_helper.rs:319-372) and is outside the B200
-// hot path: the worker reports it as unsupported instead of silently computing it elsewhere.
+// "verify --proof P --public P --vk P" runs the reference's verification equation (src/lib.rs:63-82,
+// src/proof_helper.rs:319-372) with the library's host pairing - CPU code in the reference as well.
 #include <chrono>
 #include <cstdio>
 #include <iostream>
@@ -103,8 +103,46 @@ int main()
       continue;
     }
     if (parts[0] == "verify") {
-      fprintf(stderr, "verify: not part of the B200 hot path (CPU pairing); use the reference's verifier or snarkjs\n");
-      printf("COMMAND_UNSUPPORTED\nCOMMAND_COMPLETED\n");
+      std::string proof = "proof.json", pub = "public.json", vk = "verification_key.json";
+      bool ok = true;
+      for (size_t i = 1; i < parts.size() && ok; ++i) {
+        const std::string& a = parts[i];
+        auto next = [&](std::string& dst) {
+          if (i + 1 < parts.size())
+            dst = parts[++i];
+          else
+            ok = false;
+        };
+        if (a == "--system") {
+          if (i + 1 < parts.size() && lower(parts[++i]) != "groth16") {
+            fprintf(stderr, "Unknown proof system: %s\n", parts[i].c_str());
+            ok = false;
+          }
+        } else if (a == "--proof")
+          next(proof);
+        else if (a == "--public")
+          next(pub);
+        else if (a == "--vk")
+          next(vk);
+        else
+          print_help();
+      }
+      if (!ok) {
+        print_help();
+        fflush(stdout);
+        continue;
+      }
+      int valid = 0;
+      eIcicleError e = b200_groth16_verify_files(proof.c_str(), pub.c_str(), vk.c_str(), &valid);
+      if (e != ICICLE_SUCCESS || !valid) {
+        // the reference panics here (`assert!(pairing_result, "Verification failed")` / unwrap on a bad file)
+        if (e != ICICLE_SUCCESS)
+          fprintf(stderr, "verify failed: eIcicleError %d (unreadable or malformed input file)\n", e);
+        else
+          fprintf(stderr, "Verification failed\n");
+        printf("COMMAND_FAILED\n");
+      }
+      printf("COMMAND_COMPLETED\n");
       fflush(stdout);
       continue;
     }

@@ -191,3 +191,39 @@ def groth16_prove(witness, zkey, proof, public, device, cache_manager: CacheMana
         f.write("[]" if not pub else "[\n" + ",\n".join(f'  "{x}"' for x in pub) + "\n]")
     print(f"proof took: {time.perf_counter() - start:.6f}s")
     return pr, tm
+
+
+def groth16_verify(proof, public, vk, lib=None):
+    """src/lib.rs:63-82: read proof.json, public.json, verification_key.json; four pairings; raise where the Rust code's
+    `assert!(pairing_result, "Verification failed")` panics.  Host code, as in the reference (pairing is CPU-only there)."""
+    from . import lib as _lib
+    lib = lib or _lib()
+    ok = C.c_int(0)
+    check(lib.dll.b200_groth16_verify_files(os.fsencode(proof), os.fsencode(public), os.fsencode(vk), C.byref(ok)),
+          "b200_groth16_verify_files")
+    if not ok.value:
+        raise AssertionError("Verification failed")
+
+
+def groth16_verify_points(lib, proof, public, vk):
+    """`groth16_verify_helper` (src/proof_helper.rs:319-372) on in-memory values: proof = Groth16Proof or a dict of
+    standard-form pi_a/pi_b/pi_c words, public = ints, vk = dict(alpha1, beta2, gamma2, delta2, ic).  Returns bool."""
+    if not isinstance(proof, Groth16Proof):
+        p = Groth16Proof()
+        for name in ("pi_a", "pi_b", "pi_c"):
+            arr = np.ascontiguousarray(proof[name], dtype=np.uint32).reshape(-1)
+            C.memmove(getattr(p, name), arr.ctypes.data, arr.nbytes)
+        proof = p
+    n = len(public)
+    pubs = np.zeros((max(n, 1), 8), dtype=np.uint32)
+    for i, x in enumerate(public):
+        pubs[i] = np.frombuffer(int(x).to_bytes(32, "little"), dtype=np.uint32)
+    ic = np.ascontiguousarray(vk["ic"], dtype=np.uint32)
+    if ic.shape[0] < n + 1:
+        raise ValueError(f"verification key holds {ic.shape[0]} IC points, {n + 1} needed")
+    vp = lambda a: np.ascontiguousarray(a, dtype=np.uint32).ctypes.data_as(C.c_void_p)
+    keep = [np.ascontiguousarray(vk[k], dtype=np.uint32) for k in ("alpha1", "beta2", "gamma2", "delta2")]
+    ok = C.c_int(0)
+    check(lib.dll.b200_groth16_verify(C.byref(proof), vp(keep[0]), vp(keep[1]), vp(keep[2]), vp(keep[3]), vp(ic), vp(pubs),
+                                      C.c_uint64(n), C.byref(ok)), "b200_groth16_verify")
+    return bool(ok.value)

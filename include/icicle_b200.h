@@ -50,6 +50,9 @@ typedef struct { bn254_fq_t x, y, z; } bn254_projective_t;     /* 96 B;  curves/
 typedef struct { bn254_fq_t c0, c1; } bn254_fq2_t;             /* fields/complex_extension.h */
 typedef struct { bn254_fq2_t x, y; } bn254_g2_affine_t;        /* 128 B */
 typedef struct { bn254_fq2_t x, y, z; } bn254_g2_projective_t; /* 192 B */
+typedef struct { bn254_fq2_t c[6]; } bn254_fq12_t; /* 384 B: c0.c0, c0.c1, c0.c2, c1.c0, c1.c1, c1.c2 of
+                                                     fields/snark_fields/bn254_tower.h:22-80 (Fq6 = Fq2[v]/(v^3-9-u),
+                                                     Fq12 = Fq6[w]/(w^2-v)), standard form */
 
 typedef struct { char type[64]; int id; } icicleDevice; /* 68 B; icicle/include/icicle/device.h:13-16 */
 typedef struct {                                        /* icicle/include/icicle/device_api.h DeviceProperties */
@@ -235,6 +238,18 @@ void bn254_g2_generate_projective_points(bn254_g2_projective_t* out, int size);
 void bn254_g2_generate_affine_points(bn254_g2_affine_t* out, int size);
 void bn254_g2_base_field_from_u32(uint32_t val, bn254_fq2_t* out);
 
+/* ---- pairing (CPU code in the reference as well): icicle/src/pairing.cpp:20-24 (rust icicle-core/src/pairing/
+ *      mod.rs:37-44); optimal ate, final exponentiation with the hard part of include/icicle/pairing/models/bn.h:66-100;
+ *      target-field helpers: icicle/src/fields/ffi_extern_pairing_extension.cpp:6-50 ------------------------------- */
+void bn254_pairing(const bn254_affine_t* p, const bn254_g2_affine_t* q, bn254_fq12_t* out);
+void bn254_pairing_target_field_generate_scalars(bn254_fq12_t* out, int size);
+void bn254_pairing_target_field_sub(bn254_fq12_t* a, bn254_fq12_t* b, bn254_fq12_t* out);
+void bn254_pairing_target_field_add(const bn254_fq12_t* a, const bn254_fq12_t* b, bn254_fq12_t* out);
+void bn254_pairing_target_field_mul(const bn254_fq12_t* a, const bn254_fq12_t* b, bn254_fq12_t* out);
+void bn254_pairing_target_field_inv(const bn254_fq12_t* a, bn254_fq12_t* out);
+void bn254_pairing_target_field_pow(const bn254_fq12_t* base, int exp, bn254_fq12_t* out);
+void bn254_pairing_target_field_from_u32(uint32_t val, bn254_fq12_t* out);
+
 /* ---- fused Groth16 path (shape B2 of SURVEY 8b): what the Rust groth16_prove body calls instead
  *      of the op-by-op sequence.  Replaces src/cache.rs:117-256 (ZKeyCache), src/proof_helper.rs:31-317
  *      (construct_r1cs + groth16_commitments + epilogue) and src/lib.rs:33-61. -------------------------- */
@@ -304,6 +319,18 @@ eIcicleError b200_groth16_prove_files(const char* witness_path, const char* zkey
 /* The proof.json text b200_groth16_prove_files writes for `proof` (serde_json pretty layout, src/proof_helper.rs:308-316);
  * returns its length, 0 if `cap` is too small. Host-only. */
 size_t b200_proof_to_json(const b200_groth16_proof* proof, char* out, size_t cap);
+
+/* `groth16_verify_helper` (src/proof_helper.rs:319-372): cpub = IC[0] + sum publics[i] * IC[i+1], then
+ * e(-A,B) * e(cpub,gamma_2) * e(C,delta_2) * e(alpha_1,beta_2) == 1 with four pairings on four host threads.
+ * Everything in standard form; `ic` holds n_public + 1 points. *valid = 1 / 0. Host-only, like the reference's. */
+eIcicleError b200_groth16_verify(const b200_groth16_proof* proof, const bn254_affine_t* vk_alpha_1,
+                                 const bn254_g2_affine_t* vk_beta_2, const bn254_g2_affine_t* vk_gamma_2,
+                                 const bn254_g2_affine_t* vk_delta_2, const bn254_affine_t* ic,
+                                 const bn254_scalar_t* publics, uint64_t n_public, int* valid);
+/* File-level mirror of `groth16_verify(proof, public, vk)` (src/lib.rs:63-82): reads snarkjs proof.json, public.json and
+ * verification_key.json (src/cache.rs:70-108). INVALID_ARGUMENT for unreadable / malformed files; *valid = 0 where the
+ * reference's assert!(pairing_result) would panic. */
+eIcicleError b200_groth16_verify_files(const char* proof_path, const char* public_path, const char* vk_path, int* valid);
 
 /* Synthetic-setup / test tool: out[i] = k_i * G1 (64 B affine) or k_i * G2 (128 B affine),
  * k in standard form, host or icicle_malloc'd memory; output Montgomery (as .zkey stores) or standard form.

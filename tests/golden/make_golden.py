@@ -1,6 +1,7 @@
 """Regenerates the committed Groth16 fixtures with the REFERENCE's own CPU library (oracle/_ref):
   complex_{n}.zkey / .wtns     synthetic ComplexCircuit(n,n) artefacts (tools/synth.py, seeded toxic waste)
   complex_{n}.vk.npz           verification key (standard-form affine words)
+  complex_{n}.vk.json          the same key as snarkjs's verification_key.json (what `verify --vk` reads)
   complex_{n}.proof_r1s1.json  proof.json with r = s = 1 (the reference's `no-randomness` feature)
   complex_{n}.proof_rs.json    proof.json with the fixed (r, s) below
   complex_{n}.public.json
@@ -32,6 +33,7 @@ if __name__ == "__main__":
         open(base + ".zkey", "wb").write(zkey)
         open(base + ".wtns", "wb").write(wtns)
         np.savez(base + ".vk.npz", **{k: v for k, v in vk.items() if k != "n_public"}, n_public=vk["n_public"])
+        open(base + ".vk.json", "w").write(synth.vk_json(vk))
         for tag, (r, s) in (("r1s1", (1, 1)), ("rs", (FIXED_R, FIXED_S))):
             proof, public = G.prove(ref, pkg.bindings, zkey, wtns, r, s)
             assert G.verify(ref, proof, public, vk)

@@ -157,6 +157,9 @@ def test_full_size_proof_verifies_under_reference_pairing(gpu, ref):
         assert pkg.proof_json(p1) != pkg.proof_json(p2)
         assert G.verify(ref, pkg.proof_to_dict(p1), public, vk) and G.verify(ref, pkg.proof_to_dict(p2), public, vk)
         assert not G.verify(ref, pkg.proof_to_dict(p1), [public[0] ^ 1], vk)
+        # the library's own verifier (host pairing, csrc/pairing.cu) agrees on the raw proof structs
+        assert pkg.groth16_verify_points(gpu, p1, public, vk) and pkg.groth16_verify_points(gpu, p2, public, vk)
+        assert not pkg.groth16_verify_points(gpu, p1, [public[0] ^ 1], vk)
     finally:
         cache.close()
 

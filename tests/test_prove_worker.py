@@ -27,6 +27,19 @@ def test_protocol_sentinels_without_gpu():
     assert out.rstrip().endswith("Exiting CLI worker...")
 
 
+def test_worker_verifies_golden_proofs_on_the_host(tmp_path):
+    """`verify --proof --public --vk` (main.rs:83-113,169-178): host pairing, as in the reference; a proof that does
+    not verify is reported (the Rust worker panics there) and the worker keeps serving."""
+    base = os.path.join(GOLD, "complex_100")
+    good = f"verify --proof {base}.proof_rs.json --public {base}.public.json --vk {base}.vk.json\n"
+    bad = f"verify --proof {GOLD}/complex_6.proof_rs.json --public {base}.public.json --vk {base}.vk.json\n"
+    r = run(good + "exit\n")
+    assert r.returncode == 0 and r.stdout.count("COMMAND_COMPLETED") == 2 and "COMMAND_FAILED" not in r.stdout
+    r = run(bad + good + "verify --proof\nexit\n")
+    assert r.returncode == 0 and r.stdout.count("COMMAND_COMPLETED") == 3 and r.stdout.count("COMMAND_FAILED") == 1
+    assert "Verification failed" in r.stderr and "Usage: prove [OPTIONS]" in r.stdout
+
+
 @pytest.mark.gpu
 def test_worker_proves_golden_instance(tmp_path):
     base = os.path.join(GOLD, "complex_100")
@@ -37,3 +50,6 @@ def test_worker_proves_golden_instance(tmp_path):
     assert r.returncode == 0 and r.stdout.count("COMMAND_COMPLETED") == 3 and "proof took:" in r.stdout
     assert open(proof).read() == open(base + ".proof_r1s1.json").read()
     assert open(public).read() == open(base + ".public.json").read()
+    # prove -> verify in one worker session, on the files the worker itself wrote
+    r = run(cmd + f"verify --proof {proof} --public {public} --vk {base}.vk.json\nexit\n", env=env)
+    assert r.returncode == 0 and r.stdout.count("COMMAND_COMPLETED") == 3 and "COMMAND_FAILED" not in r.stdout

@@ -259,3 +259,24 @@ def make_random_circuit(backend, n_constraints, n_inputs=64, n_public=9, max_ter
     vk = dict(alpha1=std1[0], beta2=std2[0], gamma2=std2[1], delta2=std2[2],
               ic=backend.convert_montgomery(pIC, False, kind="affine"), n_public=n_public)
     return zkey, wtns, vk
+
+
+def vk_json(vk) -> str:
+    """verification_key.json as snarkjs lays it out (the fields /root/reference/src/cache.rs:84-108 reads:
+    vk_alpha_1, vk_beta_2, vk_gamma_2, vk_delta_2, IC, nPublic; snarkjs's vk_alphabeta_12 is not used there)."""
+    import json
+
+    def dec(w):
+        return str(int.from_bytes(np.ascontiguousarray(w, dtype=np.uint32).tobytes(), "little"))
+
+    def g1(p):
+        p = np.asarray(p).reshape(-1)
+        return [dec(p[:8]), dec(p[8:16]), "1"]
+
+    def g2(p):
+        p = np.asarray(p).reshape(-1)
+        return [[dec(p[:8]), dec(p[8:16])], [dec(p[16:24]), dec(p[24:32])], ["1", "0"]]
+
+    return json.dumps({"protocol": "groth16", "curve": "bn128", "nPublic": int(vk["n_public"]),
+                       "vk_alpha_1": g1(vk["alpha1"]), "vk_beta_2": g2(vk["beta2"]), "vk_gamma_2": g2(vk["gamma2"]),
+                       "vk_delta_2": g2(vk["delta2"]), "IC": [g1(p) for p in vk["ic"]]}, indent=1)
