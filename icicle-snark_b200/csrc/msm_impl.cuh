@@ -197,12 +197,16 @@ namespace b200 {
   }
 
   // ------------------------------------------------------------------------------------------------
-  // (6) bucket reduction.  Per set: sum_b (b+1) * B_b.  Thread (set, chunk q) runs the classic running
-  // sum over REDUCE_CHUNK buckets (tot = sum (j+1) B_j, run = sum B_j) and adds (q*CHUNK)*run by a short
-  // double-and-add.  Replaces the log-halving passes of cuda_msm.cuh:846-942.
+  // (6) bucket reduction.  Per set: W = sum_b (b+1) * B_b, as a two-level running sum with no scalar multiplication
+  // on the wide level.  Level 0: thread (set, chunk q) runs the classic running sum over L0 = REDUCE_CHUNK buckets and
+  // emits T0_q = sum_j (j+1) B_{qL0+j} and R0_q = sum_j B_{qL0+j}; then W = sum_q T0_q + L0 * sum_q q R0_q.
+  // Level 1 (1/L0 of the elements): the same running sum over L2 consecutive R0 values gives T1, R1 and
+  // sum_q q R0_q = sum_q2 [T1_q2 + (L2 q2 - 1) R1_q2]; only this level pays a short double-and-add.  Its outputs,
+  // pre-multiplied by L0, are stored behind the T0 values of the set so that one tree sum finishes the set.
+  // Replaces the log-halving passes of cuda_msm.cuh:846-942.
   template <class F>
-  __global__ void __launch_bounds__(128)
-    msm_reduce_chunks_kernel(MsmDev pl, int nsel, const uint32_t* offsets, const XYZZ<F>* buckets, XYZZ<F>* chunk_sums)
+  __global__ void __launch_bounds__(128) msm_reduce_chunks_kernel(
+    MsmDev pl, int nsel, const uint32_t* offsets, const XYZZ<F>* buckets, XYZZ<F>* chunk_sums, XYZZ<F>* chunk_runs, int out_stride)
   {
     int chunks_per_set = pl.bpw / REDUCE_CHUNK;
     if (chunks_per_set == 0) chunks_per_set = 1;
@@ -220,7 +224,29 @@ namespace b200 {
         if (off[j + 1] != off[j]) xyzz_add_ni(run, ld_struct(b + j)); // empty buckets were never written
         xyzz_add_ni(tot, run);
       }
-      uint32_t base = (uint32_t)q * chunk_len;
+      st_struct(chunk_sums + (size_t)(which * pl.sets + set) * out_stride + q, tot);
+      if (chunks_per_set > 1) st_struct(chunk_runs + t, run);
+    }
+  }
+
+  // level 1 of the bucket reduction: thread (set, q2) over L2 consecutive level-0 chunk sums (see above)
+  template <class F>
+  __global__ void __launch_bounds__(128) msm_reduce_level1_kernel(
+    int nsets, int chunks_per_set, int l0_log, const XYZZ<F>* chunk_runs, XYZZ<F>* chunk_sums, int out_stride)
+  {
+    const int l2 = chunks_per_set < REDUCE_CHUNK ? chunks_per_set : REDUCE_CHUNK;
+    const int chunks2 = chunks_per_set / l2;
+    const int total = nsets * chunks2;
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
+      int set = t / chunks2, q2 = t - set * chunks2;
+      const XYZZ<F>* r = chunk_runs + (size_t)set * chunks_per_set + (size_t)q2 * l2;
+      XYZZ<F> run = XYZZ<F>::inf(), tot = XYZZ<F>::inf();
+      for (int j = l2 - 1; j >= 0; --j) {
+        xyzz_add_ni(run, ld_struct(r + j));
+        xyzz_add_ni(tot, run);
+      }
+      // tot = sum (j+1) R0_j ; wanted: sum (q2 l2 + j) R0_j = tot + (q2 l2 - 1) run
+      uint32_t base = (uint32_t)q2 * l2;
       if (base) {
         XYZZ<F> m = XYZZ<F>::inf();
         for (int bit = 31 - __clz(base); bit >= 0; --bit) {
@@ -229,7 +255,10 @@ namespace b200 {
         }
         xyzz_add_ni(tot, m);
       }
-      st_struct(chunk_sums + t, tot);
+      xyzz_add_ni(tot, run.neg());
+      for (int k = 0; k < l0_log; ++k)
+        xyzz_dbl_ni(tot);
+      st_struct(chunk_sums + (size_t)set * out_stride + chunks_per_set + q2, tot);
     }
   }
 
@@ -311,18 +340,26 @@ namespace b200 {
     const size_t max_items = sorted.max_items;
     const int chunks_per_set = plan.bpw / REDUCE_CHUNK > 0 ? plan.bpw / REDUCE_CHUNK : 1;
     const int nsets = plan.sets * nsel;
+    // level-1 outputs of the bucket reduction live behind the level-0 sums of each set
+    const int l2 = chunks_per_set < REDUCE_CHUNK ? chunks_per_set : REDUCE_CHUNK;
+    const int chunks2 = chunks_per_set > 1 ? chunks_per_set / l2 : 0;
+    const int sum_stride = chunks_per_set + chunks2;
+    int l0_log = 0;
+    while ((1 << l0_log) < (plan.bpw < REDUCE_CHUNK ? plan.bpw : REDUCE_CHUNK)) ++l0_log;
 
     auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
     size_t o_buckets = 0;
     size_t o_partials = o_buckets + al((size_t)nsel * nb * sizeof(XYZZ<F>));
     size_t o_chunks = o_partials + al((size_t)nsel * max_items * sizeof(XYZZ<F>));
-    size_t o_sets = o_chunks + al((size_t)nsets * chunks_per_set * sizeof(XYZZ<F>));
+    size_t o_runs = o_chunks + al((size_t)nsets * sum_stride * sizeof(XYZZ<F>));
+    size_t o_sets = o_runs + al((size_t)nsets * chunks_per_set * sizeof(XYZZ<F>));
     size_t total = o_sets + al((size_t)nsets * sizeof(XYZZ<F>));
     uint8_t* base = nullptr;
     B200_CUDA(cudaMallocAsync((void**)&base, total, st), ICICLE_ALLOCATION_FAILED);
     XYZZ<F>* buckets = (XYZZ<F>*)(base + o_buckets);
     XYZZ<F>* partials = (XYZZ<F>*)(base + o_partials);
     XYZZ<F>* chunk_sums = (XYZZ<F>*)(base + o_chunks);
+    XYZZ<F>* chunk_runs = (XYZZ<F>*)(base + o_runs);
     XYZZ<F>* set_sums = (XYZZ<F>*)(base + o_sets);
 
     BasesSel<F> sel;
@@ -345,18 +382,22 @@ namespace b200 {
       sorted.item_off, partials, buckets, (uint32_t)nb, (uint32_t)max_items);
     B200_LAUNCH(
       msm_reduce_chunks_kernel<F>, grid_for((size_t)nsets * chunks_per_set, 128, 16), 128, 0, st, pl, nsel, sorted.offsets, buckets,
-      chunk_sums);
+      chunk_sums, chunk_runs, sum_stride);
+    if (chunks2 > 0)
+      B200_LAUNCH(
+        msm_reduce_level1_kernel<F>, grid_for((size_t)nsets * chunks2, 128, 16), 128, 0, st, nsets, chunks_per_set, l0_log, chunk_runs,
+        chunk_sums, sum_stride);
     {
       // level 1: G CTAs per set, level 2: one CTA per set over the G partial sums
-      int G = (chunks_per_set + WSUM_BLOCK * 4 - 1) / (WSUM_BLOCK * 4);
+      int G = (sum_stride + WSUM_BLOCK * 4 - 1) / (WSUM_BLOCK * 4);
       if (G > 128) G = 128;
       if (G < 1) G = 1;
-      int per_cta = (chunks_per_set + G - 1) / G;
+      int per_cta = (sum_stride + G - 1) / G;
       const size_t sm = WSUM_BLOCK * sizeof(XYZZ<F>);
       if (G == 1) {
-        B200_LAUNCH(msm_set_sum_kernel<F>, dim3(1, nsets), WSUM_BLOCK, sm, st, chunk_sums, chunks_per_set, chunks_per_set, set_sums);
+        B200_LAUNCH(msm_set_sum_kernel<F>, dim3(1, nsets), WSUM_BLOCK, sm, st, chunk_sums, sum_stride, sum_stride, set_sums);
       } else {
-        B200_LAUNCH(msm_set_sum_kernel<F>, dim3(G, nsets), WSUM_BLOCK, sm, st, chunk_sums, chunks_per_set, per_cta, partials);
+        B200_LAUNCH(msm_set_sum_kernel<F>, dim3(G, nsets), WSUM_BLOCK, sm, st, chunk_sums, sum_stride, per_cta, partials);
         B200_LAUNCH(msm_set_sum_kernel<F>, dim3(1, nsets), WSUM_BLOCK, sm, st, partials, G, G, set_sums);
       }
     }
