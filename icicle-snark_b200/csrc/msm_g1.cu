@@ -23,20 +23,27 @@ namespace b200 {
       // every window folded into one bucket set by precomputed bases: the reduction is 1/W of the work,
       // so wider windows (fewer adds per scalar) pay
       if (c < 2) c = 2;
+      int narrow = 4;
       if (factor > 1 && lg >= 12) {
         // precomputed multiples fold the windows into few bucket sets, so the reduction is cheap and wider windows
-        // (fewer adds per scalar) pay; small inputs additionally want many short buckets so that one thread per
-        // bucket fills the machine. Prefer a width whose window count fits the factor (a single bucket set).
+        // (fewer adds per scalar) pay. Prefer a width whose window count fits the factor (a single bucket set).
+        // Measured on B200 (tools/sweep_small.sh, tools/probe_shard.py, factor 16): 2^20 points and above want
+        // c = 20; below that c = 17 wins by 5-30 % (16 windows, the top one holding only the recoding carry)
+        // because the 2^19-bucket reduction stops amortising. Widths whose top window holds 1..8 bits (18, 19, 21)
+        // lose everywhere: n / 2^bits entries land in each of a few buckets.
         int c_fit = (bitsize + 2 + factor - 1) / factor; // smallest c with windows <= factor
-        int c_wide = lg + 1 < 21 ? lg + 1 : 21;
-        if (c_fit <= 21) c = c_wide > c_fit ? c_wide : c_fit;
+        int c_wide = lg >= 20 ? (lg + 1 < 21 ? lg + 1 : 21) : 17;
+        if (c_fit <= 21) {
+          c = c_wide > c_fit ? c_wide : c_fit;
+          narrow = 8;
+        }
       }
-      // a top window holding only 1..4 bits of the scalar funnels n/2^bits entries into each of a few
+      // a top window holding only a few bits of the scalar funnels n/2^bits entries into each of a few
       // buckets; step down until the top window is either empty or reasonably wide
       while (c > 2) {
         int w = (bitsize + 2 + c - 1) / c;
         int top_bits = bitsize - c * (w - 1);
-        if (top_bits > 0 && top_bits <= 4) --c; else break;
+        if (top_bits > 0 && top_bits <= narrow) --c; else break;
       }
     }
     if (c < 2) c = 2;

@@ -11,7 +11,7 @@ namespace b200 {
     ++g_launches;                                                                                                      \
   } while (0)
 
-  static constexpr int REDUCE_CHUNK = 16; // buckets per running-sum thread
+  static constexpr int REDUCE_CHUNK = 8; // buckets per running-sum thread
   static constexpr int MSM_MAX_SEL = 4;   // base-point sets one sort can feed in a single accumulate launch
 
   template <class F>
