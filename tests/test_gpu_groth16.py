@@ -80,6 +80,15 @@ def test_fresh_instance_matches_oracle_pipeline(gpu, ref, n):
         assert tm.total_ms > 0
     finally:
         cache.close()
+    if n >= 30000:
+        # the bench's N = 8 shape in small: eight shards with precompute tables (16 windows of 17 bits, one bucket set)
+        caches = [pkg.ZKeyCache(gpu, zkey, precompute=16, rank=r, world=8) for r in range(8)]
+        try:
+            parts = [c.commit_partials(wtns_words(wtns))[0] for c in caches]
+            assert pkg.proof_json(caches[0].finish(parts, FIXED_R, FIXED_S)) == G.proof_json(proof_ref)
+        finally:
+            for c in caches:
+                c.close()
 
 
 def test_sharded_partials_fold_to_the_same_proof(gpu):
