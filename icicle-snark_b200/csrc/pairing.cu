@@ -458,18 +458,20 @@ namespace b200 {
       return true;
     }
 
+    // coordinates are JSON strings of decimal digits (serde: Vec<String>); a bare number is a type error there too
+    static bool coord_of(const Value& v, uint32_t out[8]) { return v.kind == Value::String && decimal_to_limbs(v.text, out); }
     static bool g1_of(const Value* v, G1Affine& out_std)
     {
       if (!v || v->kind != Value::Array || v->items.size() < 2) return false;
-      return decimal_to_limbs(v->items[0].text, out_std.x.v) && decimal_to_limbs(v->items[1].text, out_std.y.v);
+      return coord_of(v->items[0], out_std.x.v) && coord_of(v->items[1], out_std.y.v);
     }
     static bool g2_of(const Value* v, G2Affine& out_std)
     {
       if (!v || v->kind != Value::Array || v->items.size() < 2) return false;
       const Value &x = v->items[0], &y = v->items[1];
-      if (x.items.size() < 2 || y.items.size() < 2) return false;
-      return decimal_to_limbs(x.items[0].text, out_std.x.c0.v) && decimal_to_limbs(x.items[1].text, out_std.x.c1.v) &&
-             decimal_to_limbs(y.items[0].text, out_std.y.c0.v) && decimal_to_limbs(y.items[1].text, out_std.y.c1.v);
+      if (x.kind != Value::Array || y.kind != Value::Array || x.items.size() < 2 || y.items.size() < 2) return false;
+      return coord_of(x.items[0], out_std.x.c0.v) && coord_of(x.items[1], out_std.x.c1.v) &&
+             coord_of(y.items[0], out_std.y.c0.v) && coord_of(y.items[1], out_std.y.c1.v);
     }
   } // namespace vjson
 
@@ -606,7 +608,8 @@ EXPORT eIcicleError b200_groth16_verify_files(const char* proof_path, const char
     if (!read_file(paths[k], text[k])) return ICICLE_INVALID_ARGUMENT;
     Reader rd(text[k]);
     doc[k] = rd.value();
-    if (!rd.ok) return ICICLE_INVALID_ARGUMENT;
+    rd.ws();
+    if (!rd.ok || rd.i != text[k].size()) return ICICLE_INVALID_ARGUMENT; // malformed, or trailing characters
   }
   const Value &pj = doc[0], &pub = doc[1], &vk = doc[2];
   b200_groth16_proof proof;
@@ -629,7 +632,7 @@ EXPORT eIcicleError b200_groth16_verify_files(const char* proof_path, const char
     if (!g1_of(&icv->items[i], ic[i])) return ICICLE_INVALID_ARGUMENT;
   std::vector<Fr> publics(used);
   for (size_t i = 0; i < used; ++i)
-    if (!decimal_to_limbs(pub.items[i].text, publics[i].v)) return ICICLE_INVALID_ARGUMENT;
+    if (!coord_of(pub.items[i], publics[i].v)) return ICICLE_INVALID_ARGUMENT;
   return b200_groth16_verify(
     &proof, reinterpret_cast<const bn254_affine_t*>(&alpha1), reinterpret_cast<const bn254_g2_affine_t*>(&beta2),
     reinterpret_cast<const bn254_g2_affine_t*>(&gamma2), reinterpret_cast<const bn254_g2_affine_t*>(&delta2),

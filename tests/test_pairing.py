@@ -117,5 +117,22 @@ def test_verify_files_mirror(lib, tmp_path):
     novk.write_text(json.dumps(d))
     with pytest.raises(pkg.IcicleError):
         pkg.groth16_verify(base + ".proof_r1s1.json", base + ".public.json", str(novk), lib=lib)
+    # serde's typing: coordinates are strings (a bare JSON number is an error), nothing may follow the document
+    nums = tmp_path / "public_numbers.json"
+    nums.write_text("[" + ", ".join(json.load(open(base + ".public.json"))) + "]")
+    with pytest.raises(pkg.IcicleError):
+        pkg.groth16_verify(base + ".proof_r1s1.json", str(nums), base + ".vk.json", lib=lib)
+    trailing = tmp_path / "proof_trailing.json"
+    trailing.write_text(open(base + ".proof_r1s1.json").read() + " x")
+    with pytest.raises(pkg.IcicleError):
+        pkg.groth16_verify(str(trailing), base + ".public.json", base + ".vk.json", lib=lib)
+    # extra public values are ignored (`public.iter().take(n_public)`), as is snarkjs's vk_alphabeta_12
+    extra = tmp_path / "public_extra.json"
+    extra.write_text(json.dumps(json.load(open(base + ".public.json")) + ["5"]))
+    d = json.load(open(base + ".vk.json"))
+    d["vk_alphabeta_12"] = [[["1", "2"], ["3", "4"], ["5", "6"]], [["7", "8"], ["9", "10"], ["11", "12"]]]
+    vk2 = tmp_path / "vk_snarkjs.json"
+    vk2.write_text(json.dumps(d, indent=1))
+    pkg.groth16_verify(base + ".proof_r1s1.json", str(extra), str(vk2), lib=lib)
     ok = C.c_int(7)
     assert lib.dll.b200_groth16_verify_files(None, None, None, C.byref(ok)) == pkg.ERRORS.index("INVALID_POINTER")
