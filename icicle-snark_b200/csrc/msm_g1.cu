@@ -76,6 +76,22 @@ using namespace b200;
 
 extern "C" {
 
+// host-only: the plan the MSM entry points and the ZKeyCache derive for a shape (window width heuristic, window count,
+// bucket sets after precompute folding, recoding constant); lets the CPU tests check the host logic without a GPU
+eIcicleError b200_msm_plan_info(int n, int c, int bitsize, int precompute_factor, int g2, int32_t* out8, uint32_t* hconst9)
+{
+  if (!out8) return ICICLE_INVALID_POINTER;
+  if (n < 1 || bitsize < 1 || bitsize > 254 || c < 0 || c > 22) return ICICLE_INVALID_ARGUMENT;
+  MsmPlan p = make_msm_plan(n, c, bitsize, precompute_factor, g2 != 0);
+  const int32_t v[8] = {p.c, p.windows, p.factor, p.sets, p.bpw, p.nbuckets, p.item_cap, p.n};
+  for (int i = 0; i < 8; ++i)
+    out8[i] = v[i];
+  if (hconst9)
+    for (int i = 0; i < 9; ++i)
+      hconst9[i] = p.hconst[i];
+  return ICICLE_SUCCESS;
+}
+
 eIcicleError bn254_msm(
   const bn254_scalar_t* scalars, const bn254_affine_t* bases, int msm_size, const MSMConfig* config, bn254_projective_t* results)
 {

@@ -341,6 +341,11 @@ eIcicleError b200_fixed_base_mul(const bn254_scalar_t* k, uint64_t n, int g2, in
  * 4 IMAD.WIDE+DFMA co-issue, 5 carry-chained wide multiply-adds. b200_imad_peak(wide) = mode 5 / mode 0. */
 double b200_pipe_peak(int mode);
 double b200_imad_peak(int wide);
+/* The Pippenger plan derived for an MSM shape (host-only; same code path as bn254_msm and the ZKeyCache):
+ * out8 = {c, windows, factor, sets, buckets per set, buckets, work-item cap, n}; hconst9 (optional) = the 288-bit
+ * signed-digit recoding constant sum_w 2^(c-1) 2^(c w). c = 0 asks for the heuristic (the reference's is
+ * backend/cuda/src/msm/cuda_msm.cuh:45-48). */
+eIcicleError b200_msm_plan_info(int n, int c, int bitsize, int precompute_factor, int g2, int32_t* out8, uint32_t* hconst9);
 /* kernel launches issued by this library since load (bench.py's gpu_launches) */
 unsigned long long b200_launch_count(void);
 /* CUDA-event timing of the MSM bucket-accumulation kernel (the dominant kernel) for bench.py's roofline:
