@@ -143,6 +143,9 @@ def main():
     ap.add_argument("--precompute", type=int, default=int(os.environ.get("B200_PRECOMPUTE", "16")))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--split-quotient", type=int, default=1, help="N>1: split the three quotient polynomials across ranks (0 = replicate)")
+    ap.add_argument("--shard-skew", type=float, default=0.049,
+                    help="N>1 with the quotient split: the polynomial owners get smaller witness-MSM shards "
+                         "(b200_shard_range; = one polynomial's transform time / all witness MSMs' time; 0 = equal shards)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -174,6 +177,11 @@ def main():
     if rank == 0:
         log(f"synthetic instance: {len(zkey) / 1e6:.0f} MB zkey in {time.time() - t0:.1f}s")
     t_cache = time.time()
+    skew = args.shard_skew if (world > 1 and args.split_quotient) else 0.0
+    if skew > 0:
+        os.environ["B200_SHARD_SKEW"] = repr(skew)  # read by the library when it cuts the cache's witness shards
+    else:
+        os.environ.pop("B200_SHARD_SKEW", None)
     cache = pkg.ZKeyCache(lib, zkey, precompute=args.precompute, rank=rank, world=world)
     lib.device_synchronize()
     t_cache = time.time() - t_cache  # cold path: parse + H2D + precompute tables + CSR + coset powers + twiddles
@@ -316,7 +324,7 @@ def main():
         "warmup": args.warmup, "ms_per_step": ms_dev, "higher_is_better": False, "scaling": "strong", "vs_baseline": None,
         "dtype": "u32x8 (254-bit modular integers)", "data": "synthetic",
         "config": {"workload": f"ComplexCircuit({n},{n}) Groth16 prove, warm ZKeyCache", "n_vars": cache.n_vars,
-                   "domain_size": cache.domain_size, "precompute_factor": args.precompute, "parallelism": f"msm-shard{world}" + ("+quotient-split" if qx is not None else ""),
+                   "domain_size": cache.domain_size, "precompute_factor": args.precompute, "parallelism": f"msm-shard{world}" + ("+quotient-split" if qx is not None else "") + (f"+shard-skew{skew:g}" if skew > 0 else ""),
                    "l2": "256 MiB flush between timed iterations", "timing": "host clock around the synchronous C-ABI call + cuda sync + barrier, max over ranks"},
         "e2e": {"value": ms_e2e, "unit": "ms", "h2d_bytes_per_step": nw * 32, "d2h_bytes_per_step": 576 if world == 1 else 576 * world,
                 "note": "h2d bytes are per rank that evaluates R1CS rows (all ranks when the quotient chain is replicated; the 3 polynomial owners when it is split, the others upload only their 1/N witness slice)"},

@@ -195,6 +195,41 @@ namespace b200 {
     *hi = (uint32_t)((uint64_t)n * (rank + 1) / world);
   }
 
+  // quotient polynomials rank `rank` transforms when the chain is split (must match multi_gpu.poly_owner)
+  static int polys_owned(int rank, int world)
+  {
+    if (world >= 3) return rank < 3 ? 1 : 0;
+    if (world == 2) return rank == 0 ? 2 : 1;
+    return 3;
+  }
+
+  // Witness-MSM shard of `rank` when the quotient chain is split across ranks: the polynomial owners carry the
+  // transforms on top of their MSM shard, so they get a smaller one.  share(r) = 1/world + (3/world - polys(r)) * skew,
+  // skew = (time of one polynomial's iNTT + NTT) / (time of all witness MSMs on one GPU); skew = 0 is the equal split.
+  static void shard_skewed(uint32_t n, int rank, int world, double skew, uint32_t* lo, uint32_t* hi)
+  {
+    if (!(skew > 0) || world < 2) return shard(n, rank, world, lo, hi);
+    if (skew > 0.2) skew = 0.2;
+    double acc = 0, bounds[65];
+    if (world > 64) return shard(n, rank, world, lo, hi);
+    bounds[0] = 0;
+    for (int r = 0; r < world; ++r) {
+      double share = 1.0 / world + (3.0 / world - polys_owned(r, world)) * skew;
+      if (share <= 0) return shard(n, rank, world, lo, hi); // too few ranks for this skew: equal split
+      acc += share;
+      bounds[r + 1] = acc;
+    }
+    auto at = [&](int r) {
+      if (r <= 0) return (uint32_t)0;
+      if (r >= world) return n;
+      uint64_t v = (uint64_t)((double)n * (bounds[r] / acc) + 0.5);
+      return (uint32_t)(v > n ? n : v);
+    };
+    *lo = at(rank);
+    *hi = at(rank + 1);
+    if (*hi < *lo) *hi = *lo;
+  }
+
   static void cache_free(b200_zkey_cache* c)
   {
     if (!c) return;
@@ -378,7 +413,9 @@ namespace b200 {
     // ---- base points: this rank's contiguous shard of every section
     // A, B1, B2 and C (padded in front with n_public+1 points at infinity) are all indexed by signal, so the four
     // witness MSMs share one shard range, one plan and one sort
-    shard(c->n_vars, rank, world, &c->a_lo, &c->a_hi);
+    // B200_SHARD_SKEW (set by a caller that splits the quotient chain, see shard_skewed): every rank must use the same value
+    const char* sk_env = getenv("B200_SHARD_SKEW");
+    shard_skewed(c->n_vars, rank, world, sk_env ? atof(sk_env) : 0.0, &c->a_lo, &c->a_hi);
     c->c_lo = c->a_lo;
     c->c_hi = c->a_hi;
     shard(N, rank, world, &c->h_lo, &c->h_hi);
@@ -931,6 +968,14 @@ eIcicleError b200_zkey_cache_b_points(const b200_zkey_cache* c, uint32_t* kept, 
   if (!c || !kept || !total) return ICICLE_INVALID_POINTER;
   *kept = c->n_b;
   *total = c->a_hi - c->a_lo;
+  return ICICLE_SUCCESS;
+}
+
+eIcicleError b200_shard_range(uint32_t n, int rank, int world, double skew, uint32_t* lo, uint32_t* hi)
+{
+  if (!lo || !hi) return ICICLE_INVALID_POINTER;
+  if (world < 1 || rank < 0 || rank >= world) return ICICLE_INVALID_ARGUMENT;
+  shard_skewed(n, rank, world, skew, lo, hi);
   return ICICLE_SUCCESS;
 }
 

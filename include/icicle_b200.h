@@ -304,6 +304,11 @@ eIcicleError b200_groth16_commit_begin(b200_zkey_cache* cache, const bn254_scala
 eIcicleError b200_groth16_commit_end(b200_zkey_cache* cache, const void* a_dev, const void* b_dev, const void* c_dev,
                                      b200_groth16_partials* out, b200_prove_timings* timings);
 eIcicleError b200_zkey_cache_h_range(const b200_zkey_cache* cache, uint32_t* lo, uint32_t* hi);
+/* Shard [lo, hi) of an n-element section for `rank` of `world` (host-only). skew = 0: the equal contiguous split used
+ * for the H section (and for everything when the quotient chain is replicated). skew > 0: the split used for the
+ * signal-indexed sections (A, B1, B2, C) when B200_SHARD_SKEW is set - ranks that transform quotient polynomials get
+ * share 1/world + (3/world - polys_owned) * skew, so all ranks finish together. */
+eIcicleError b200_shard_range(uint32_t n, int rank, int world, double skew, uint32_t* lo, uint32_t* hi);
 /* B1/B2 points kept in this rank's shard after dropping the columns at infinity (signals absent from every B row; dropped
  * when they are >= 1/8 of the shard, B200_SPARSE_B=0/1 overrides) and the shard's signal count. */
 eIcicleError b200_zkey_cache_b_points(const b200_zkey_cache* cache, uint32_t* kept, uint32_t* total);

@@ -107,6 +107,24 @@ def test_sharded_partials_fold_to_the_same_proof(gpu):
             c.close()
 
 
+def test_skewed_shards_fold_to_the_same_proof(gpu, monkeypatch):
+    # B200_SHARD_SKEW (bench.py sets it when the quotient chain is split): polynomial owners hold smaller witness shards;
+    # any partition must fold to the same proof
+    zkey, wtns, vk, gold11, goldrs, _ = load(100)
+    w = wtns_words(wtns)
+    monkeypatch.setenv("B200_SHARD_SKEW", "0.1")
+    caches = [pkg.ZKeyCache(gpu, zkey, precompute=p, rank=r, world=4) for r, p in zip(range(4), (1, 16, 1, 16))]
+    try:
+        sizes = [c.b_points()[1] for c in caches]
+        assert sum(sizes) == caches[0].n_vars and sizes[3] > sizes[0] and sizes[0] == sizes[1] == sizes[2]
+        assert [c.h_range() for c in caches] == [pkg.multi_gpu.shard_range(caches[0].domain_size, r, 4) for r in range(4)]
+        parts = [c.commit_partials(w)[0] for c in caches]
+        assert pkg.proof_json(caches[0].finish(parts, FIXED_R, FIXED_S)) == goldrs
+    finally:
+        for c in caches:
+            c.close()
+
+
 def test_fixed_base_tool_against_reference(gpu, ref, rng):
     from util import rand_scalars
     k, _ = rand_scalars(rng, 50)

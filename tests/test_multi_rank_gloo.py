@@ -88,3 +88,38 @@ def test_shard_ranges_partition():
             r = [pkg.multi_gpu.shard_range(n, k, world) for k in range(world)]
             assert r[0][0] == 0 and r[-1][1] == n
             assert all(r[k][1] == r[k + 1][0] for k in range(world - 1))
+
+
+def test_skewed_witness_shards_partition_and_balance(lib):
+    """b200_shard_range: the split the library uses for the signal-indexed sections when the quotient chain is split
+    (B200_SHARD_SKEW). Always a partition of [0, n); skew 0 equals the plain split; with skew s the polynomial owners'
+    shares are smaller by exactly s of the total per owned polynomial."""
+    import ctypes as C
+    import icicle_snark_b200 as pkg
+
+    def rng(n, rank, world, skew):
+        lo, hi = C.c_uint32(), C.c_uint32()
+        assert lib.dll.b200_shard_range(C.c_uint32(n), rank, world, C.c_double(skew), C.byref(lo), C.byref(hi)) == 0
+        return lo.value, hi.value
+
+    for n in (0, 1, 7, 100, 3_200_002):
+        for world in (1, 2, 3, 4, 8):
+            for skew in (0.0, 0.049, 0.1, 0.2, 5.0):
+                r = [rng(n, k, world, skew) for k in range(world)]
+                assert r[0][0] == 0 and r[-1][1] == n
+                assert all(r[k][1] == r[k + 1][0] and r[k][0] <= r[k][1] for k in range(world - 1))
+                if skew == 0.0:
+                    assert r == [pkg.multi_gpu.shard_range(n, k, world) for k in range(world)]
+    n = 3_200_002
+    for world in (2, 4, 8):
+        sizes = [hi - lo for lo, hi in (rng(n, k, world, 0.049) for k in range(world))]
+        owned = [pkg.multi_gpu.owned_polys(k, world)[1] for k in range(world)]
+        for k in range(world):
+            want = n * (1.0 / world + (3.0 / world - owned[k]) * 0.049)
+            assert abs(sizes[k] - want) <= 2, (world, k, sizes, want)
+        # model: time = polys * skew + share is the same on every rank
+        t = [owned[k] * 0.049 + sizes[k] / n for k in range(world)]
+        assert max(t) - min(t) < 1e-5
+    lo, hi = C.c_uint32(), C.c_uint32()
+    assert lib.dll.b200_shard_range(C.c_uint32(10), 3, 3, C.c_double(0.0), C.byref(lo), C.byref(hi)) == 11
+    assert lib.dll.b200_shard_range(C.c_uint32(10), 0, 1, C.c_double(0.0), None, C.byref(hi)) == 3
