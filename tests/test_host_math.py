@@ -2,6 +2,7 @@
 the prover epilogue's only arithmetic) against the reference's compiled frontend. These run the SAME
 field/curve templates (csrc/field.cuh, csrc/curve.cuh) the device kernels instantiate, on the host."""
 import numpy as np
+import pytest
 
 from oracle import bn254_py as O
 from util import R, Q, from_words, g1_points_multiples, g2_points_multiples, rand_scalars, to_words
@@ -86,3 +87,20 @@ def test_python_oracle_agrees_with_host_helpers(lib, rng):
         assert got == O.G1.mul(O.G1_GEN, sv[i])
         got2 = O.g2_projective_words_to_affine(list(lib.mul_scalar(lib.generator(g2=True), sc[i], g2=True)))
         assert got2 == O.G2.mul(O.G2.gen, sv[i])
+
+
+@pytest.mark.parametrize("g2", [0, 1])
+def test_batched_affine_bucket_model_matches_xyzz_accumulation(lib, g2):
+    """csrc/batch_affine.cuh + batch_affine_model.cu (DESIGN.md section 8.1, next kernel generation): pairwise-tree rounds
+    with Montgomery's trick reproduce the bucket sums of today's XYZZ accumulation on data with repeated points
+    (tangent case), opposite points (cancellation), identities, empty buckets and one giant bucket - and spend fewer
+    than 8 field products per addition where the XYZZ mixed add spends 10."""
+    import ctypes as C
+    f = lib.dll.b200_batch_affine_selfcheck
+    for n, nb, m, m2 in ((0, 4, 16, 64), (1, 1, 16, 64), (2, 1, 16, 64), (5000, 37, 16, 64), (20000, 512, 16, 64),
+                         (3000, 3, 1, 1), (4000, 64, 7, 5), (9000, 1000, 32, 8)):
+        ppa = C.c_double(0)
+        assert f(g2, n, nb, m, m2, 99 + n, C.byref(ppa)) == 0, (n, nb, m, m2)
+        if n >= 5000 and m >= 16:
+            assert 6.0 < ppa.value < 8.0, ppa.value
+    assert f(g2, -1, 4, 16, 64, 0, None) == -1 and f(g2, 10, 0, 16, 64, 0, None) == -1
