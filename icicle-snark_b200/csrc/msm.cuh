@@ -66,6 +66,8 @@ namespace b200 {
     MsmItem* sorted = nullptr;     // work items, longest first
     size_t max_items = 0;
   };
+  // out[0..n] = exclusive scan of in[0..n), out[n] = total; tile_sums: >= n / 4096 + 2 words of scratch (msm_sort.cu)
+  void msm_exclusive_scan(const uint32_t* in, int n, uint32_t* out, uint32_t* tile_sums, cudaStream_t st);
   eIcicleError msm_sort_enqueue(const MsmPlan& plan, const Fr* scalars, bool scalars_mont, MsmSorted* out, cudaStream_t st);
   void msm_sorted_free(MsmSorted* s, cudaStream_t st);
 

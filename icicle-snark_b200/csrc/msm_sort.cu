@@ -159,6 +159,11 @@ namespace b200 {
     B200_LAUNCH(scan_add_kernel, ntiles, SCAN_BLOCK, 0, st, out, n, tile_sums, tile_sums + ntiles);
   }
 
+  void msm_exclusive_scan(const uint32_t* in, int n, uint32_t* out, uint32_t* tile_sums, cudaStream_t st)
+  {
+    exclusive_scan(in, n, out, tile_sums, st);
+  }
+
   // ------------------------------------------------------------------------------------------------
   // (3) scatter point references into bucket order, window-major so the write window stays in L2.
   // entries[pos] = (i*f + w/sets) | sign<<31.  cursor starts as a copy of the exclusive offsets.

@@ -352,11 +352,12 @@ double b200_imad_peak(int wide);
  * backend/cuda/src/msm/cuda_msm.cuh:45-48). */
 eIcicleError b200_msm_plan_info(int n, int c, int bitsize, int precompute_factor, int g2, int32_t* out8, uint32_t* hconst9);
 /* HOST model of bucket accumulation by batched affine addition (csrc/batch_affine_model.cu; DESIGN.md section 8.1, the
- * round-2 arithmetic item): pairwise-tree rounds with Montgomery's trick in per-thread chunks of m slots and a second
- * level over m2 chunk totals, checked against the XYZZ accumulation the MSM uses today. Returns the number of
- * mismatching buckets (0 = agreement; -1 = bad arguments); *products_per_add = field products per real addition.
- * Test infrastructure for the next kernel generation - no kernel uses it. */
-int b200_batch_affine_selfcheck(int g2, int n_entries, int n_buckets, int m, int m2, unsigned seed, double* products_per_add);
+ * round-2 arithmetic item): pairwise-tree rounds with a two-level Montgomery trick, executed with the same per-thread
+ * bodies (csrc/batch_affine.cuh) the experimental kernels wrap, checked against the XYZZ accumulation the MSM uses today.
+ * max_rounds < 0: run to completion; otherwise stop after that many rounds and sum the leftovers serially. Returns the
+ * number of mismatching buckets (0 = agreement; -1 = bad arguments); *products_per_add = field products per real
+ * addition. Test infrastructure for the next kernel generation. */
+int b200_batch_affine_selfcheck(int g2, int n_entries, int n_buckets, int max_rounds, unsigned seed, double* products_per_add);
 /* kernel launches issued by this library since load (bench.py's gpu_launches) */
 unsigned long long b200_launch_count(void);
 /* CUDA-event timing of the MSM bucket-accumulation kernel (the dominant kernel) for bench.py's roofline:
