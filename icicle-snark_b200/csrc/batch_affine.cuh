@@ -232,4 +232,95 @@ namespace b200 {
     return true;
   }
 
+  // ------------------------------------------------------------------------------------------------------------
+  // The round driver, shared by the kernels' host-side launcher (msm_batch_affine.cuh) and the host model: buffer
+  // planes for up to BA_MAX_SEL base-point tables that share one sort, ping-pong of the point and offset arrays, and
+  // the slot bounds the grids are sized with.  `Exec` runs one pass for `threads` threads of every selection.
+  static constexpr int BA_MAX_SEL = 4;
+
+  template <class F>
+  struct BaLaunch {
+    int round0, nb;
+    const uint32_t* entries;
+    const Affine<F>* tables[BA_MAX_SEL];
+    const Affine<F>* cur;
+    Affine<F>* nxt;
+    size_t pts_stride; // elements per selection in cur / nxt / prefix
+    const uint32_t* off;
+    const uint32_t* off_next;
+    F* prefix;
+    F* totals;
+    size_t tot_stride; // elements per selection in totals
+  };
+
+  template <class F>
+  B200_HD BaRound<F> ba_round_of(const BaLaunch<F>& L, int which)
+  {
+    BaRound<F> R;
+    R.round0 = L.round0;
+    R.entries = L.entries;
+    R.table = L.tables[which];
+    R.cur = L.cur + (size_t)which * L.pts_stride;
+    R.off = L.off;
+    R.off_next = L.off_next;
+    R.nb = L.nb;
+    R.prefix = L.prefix + (size_t)which * L.pts_stride;
+    R.totals = L.totals + (size_t)which * L.tot_stride;
+    R.nxt = L.nxt + (size_t)which * L.pts_stride;
+    return R;
+  }
+
+  // a round's output has at most ceil(E_in / 2) + nb slots (one copied tail per bucket)
+  inline size_t ba_slot_bound(size_t e_in, int nb) { return (e_in + 1) / 2 + (size_t)nb; }
+  inline size_t ba_threads_for(size_t slots) { return (slots + BA_M - 1) / BA_M; }
+
+  struct BaResult { // where the last round left the bucket segments
+    const uint32_t* off;
+    const void* cur;
+    size_t pts_stride;
+  };
+
+  // pts0/pts1: nsel * ba_slot_bound(E, nb) points each; prefix: as many field elements; totals: nsel *
+  // ba_threads_for(that bound); off0/off1: nb + 1 words each
+  template <class F, class Exec>
+  BaResult ba_run_rounds(
+    Exec& ex, size_t E, int nb, int nsel, int rounds, const uint32_t* entries, const Affine<F>* const* tables,
+    const uint32_t* offsets0, Affine<F>* pts0, Affine<F>* pts1, F* prefix, F* totals, uint32_t* off0, uint32_t* off1)
+  {
+    const size_t slots0 = ba_slot_bound(E, nb);
+    Affine<F>* pts[2] = {pts0, pts1};
+    uint32_t* offs[2] = {off0, off1};
+    BaLaunch<F> L;
+    L.nb = nb;
+    L.entries = entries;
+    for (int k = 0; k < BA_MAX_SEL; ++k)
+      L.tables[k] = tables[k < nsel ? k : 0];
+    L.pts_stride = slots0;
+    L.prefix = prefix;
+    L.totals = totals;
+    L.tot_stride = ba_threads_for(slots0);
+    const uint32_t* off = offsets0;
+    const Affine<F>* cur = pts[1]; // not read in round 0
+    size_t in_bound = E;
+    for (int r = 0; r < rounds; ++r) {
+      uint32_t* off_next = offs[r & 1];
+      Affine<F>* nxt = pts[r & 1];
+      ex.next_offsets(off, nb, off_next); // off_next = exclusive scan of ceil(len / 2), total in off_next[nb]
+      const size_t out_bound = ba_slot_bound(in_bound, nb);
+      const size_t threads = ba_threads_for(out_bound);
+      L.round0 = r == 0;
+      L.cur = cur;
+      L.nxt = nxt;
+      L.off = off;
+      L.off_next = off_next;
+      ex.prefix(L, threads, nsel);
+      ex.invert(L, (threads + BA_M2 - 1) / BA_M2, nsel);
+      ex.finish(L, threads, nsel);
+      off = off_next;
+      cur = nxt;
+      if (out_bound < in_bound) in_bound = out_bound;
+    }
+    return {off, cur, slots0};
+  }
+
 } // namespace b200

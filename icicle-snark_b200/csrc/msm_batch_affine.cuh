@@ -21,38 +21,6 @@ namespace b200 {
   }
 
   template <class F>
-  struct BaLaunch { // one round for up to MSM_MAX_SEL selections (blockIdx.y): planes of the per-slot arrays
-    int round0, nb;
-    const uint32_t* entries;
-    BasesSel<F> sel;
-    const Affine<F>* cur;
-    Affine<F>* nxt;
-    size_t pts_stride; // elements per selection in cur / nxt / prefix
-    const uint32_t* off;
-    const uint32_t* off_next;
-    F* prefix;
-    F* totals;
-    size_t tot_stride; // elements per selection in totals
-  };
-
-  template <class F>
-  __device__ __forceinline__ BaRound<F> ba_round_of(const BaLaunch<F>& L, int which)
-  {
-    BaRound<F> R;
-    R.round0 = L.round0;
-    R.entries = L.entries;
-    R.table = L.sel.p[which];
-    R.cur = L.cur + (size_t)which * L.pts_stride;
-    R.off = L.off;
-    R.off_next = L.off_next;
-    R.nb = L.nb;
-    R.prefix = L.prefix + (size_t)which * L.pts_stride;
-    R.totals = L.totals + (size_t)which * L.tot_stride;
-    R.nxt = L.nxt + (size_t)which * L.pts_stride;
-    return R;
-  }
-
-  template <class F>
   __global__ void __launch_bounds__(128) ba_prefix_kernel(BaLaunch<F> L)
   {
     BaRound<F> R = ba_round_of(L, blockIdx.y);
@@ -103,17 +71,41 @@ namespace b200 {
     return rounds;
   }
 
+  // launches one pass per call; grids are sized with the host-side slot bounds, the kernels read the true counts
+  template <class F>
+  struct BaDeviceExec {
+    cudaStream_t st;
+    uint32_t* lens;
+    uint32_t* tiles;
+    void next_offsets(const uint32_t* off, int nb, uint32_t* off_next)
+    {
+      B200_LAUNCH(ba_halve_kernel, grid_for(nb, 256, 8), 256, 0, st, off, nb, lens);
+      msm_exclusive_scan(lens, nb, off_next, tiles, st);
+    }
+    void prefix(const BaLaunch<F>& L, size_t threads, int nsel)
+    {
+      B200_LAUNCH(ba_prefix_kernel<F>, dim3(grid_for(threads, 128, 16), nsel), 128, 0, st, L);
+    }
+    void invert(const BaLaunch<F>& L, size_t threads, int nsel)
+    {
+      B200_LAUNCH(ba_invert_kernel<F>, dim3(grid_for(threads, 128, 16), nsel), 128, 0, st, L);
+    }
+    void finish(const BaLaunch<F>& L, size_t threads, int nsel)
+    {
+      B200_LAUNCH(ba_finish_kernel<F>, dim3(grid_for(threads, 128, 16), nsel), 128, 0, st, L);
+    }
+  };
+
   // buckets[which * nb + b] = sum of the bucket's points for every selection, for all non-empty buckets
   template <class F>
   eIcicleError msm_accumulate_batched_enqueue(
     const MsmPlan& plan, const MsmSorted& sorted, const BasesSel<F>& sel, int nsel, int rounds, XYZZ<F>* buckets, cudaStream_t st)
   {
+    static_assert(BA_MAX_SEL == MSM_MAX_SEL, "selection planes");
     const size_t E = plan.entries();
     const int nb = plan.nbuckets;
-    if (E >= (1ull << 31) || rounds < 1) return ICICLE_INVALID_ARGUMENT;
-    // a round's output has at most ceil(E_in / 2) + nb slots (one copied tail per bucket)
-    const size_t slots0 = (E + 1) / 2 + (size_t)nb;
-    const size_t thr0 = (slots0 + BA_M - 1) / BA_M;
+    if (E >= (1ull << 31) || rounds < 1 || nsel < 1 || nsel > BA_MAX_SEL) return ICICLE_INVALID_ARGUMENT;
+    const size_t slots0 = ba_slot_bound(E, nb), thr0 = ba_threads_for(slots0);
     const int scan_tiles = nb / 4096 + 4;
 
     auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
@@ -128,42 +120,14 @@ namespace b200 {
     size_t total = o_tiles + al((size_t)scan_tiles * 4);
     uint8_t* base = nullptr;
     B200_CUDA(cudaMallocAsync((void**)&base, total, st), ICICLE_ALLOCATION_FAILED);
-    Affine<F>* pts[2] = {(Affine<F>*)(base + o_pts0), (Affine<F>*)(base + o_pts1)};
-    uint32_t* offs[2] = {(uint32_t*)(base + o_off0), (uint32_t*)(base + o_off1)};
-    uint32_t* lens = (uint32_t*)(base + o_len);
-    uint32_t* tiles = (uint32_t*)(base + o_tiles);
 
-    BaLaunch<F> L;
-    L.nb = nb;
-    L.entries = sorted.entries;
-    L.sel = sel;
-    L.pts_stride = slots0;
-    L.prefix = (F*)(base + o_prefix);
-    L.totals = (F*)(base + o_totals);
-    L.tot_stride = thr0;
-    const uint32_t* off = sorted.offsets;
-    const Affine<F>* cur = pts[1]; // unused in round 0
-    size_t in_bound = E;
-    for (int r = 0; r < rounds; ++r) {
-      uint32_t* off_next = offs[r & 1];
-      Affine<F>* nxt = pts[r & 1];
-      B200_LAUNCH(ba_halve_kernel, grid_for(nb, 256, 8), 256, 0, st, off, nb, lens);
-      msm_exclusive_scan(lens, nb, off_next, tiles, st);
-      const size_t out_bound = (in_bound + 1) / 2 + (size_t)nb;
-      const size_t threads = (out_bound + BA_M - 1) / BA_M;
-      L.round0 = r == 0;
-      L.cur = cur;
-      L.nxt = nxt;
-      L.off = off;
-      L.off_next = off_next;
-      B200_LAUNCH(ba_prefix_kernel<F>, dim3(grid_for(threads, 128, 16), nsel), 128, 0, st, L);
-      B200_LAUNCH(ba_invert_kernel<F>, dim3(grid_for((threads + BA_M2 - 1) / BA_M2, 128, 16), nsel), 128, 0, st, L);
-      B200_LAUNCH(ba_finish_kernel<F>, dim3(grid_for(threads, 128, 16), nsel), 128, 0, st, L);
-      off = off_next;
-      cur = nxt;
-      in_bound = out_bound < in_bound ? out_bound : in_bound;
-    }
-    B200_LAUNCH(ba_buckets_kernel<F>, dim3(grid_for(nb, 128, 16), nsel), 128, 0, st, off, cur, slots0, nb, buckets);
+    BaDeviceExec<F> ex{st, (uint32_t*)(base + o_len), (uint32_t*)(base + o_tiles)};
+    BaResult res = ba_run_rounds<F>(
+      ex, E, nb, nsel, rounds, sorted.entries, sel.p, sorted.offsets, (Affine<F>*)(base + o_pts0), (Affine<F>*)(base + o_pts1),
+      (F*)(base + o_prefix), (F*)(base + o_totals), (uint32_t*)(base + o_off0), (uint32_t*)(base + o_off1));
+    B200_LAUNCH(
+      ba_buckets_kernel<F>, dim3(grid_for(nb, 128, 16), nsel), 128, 0, st, res.off, (const Affine<F>*)res.cur, res.pts_stride, nb,
+      buckets);
     cudaError_t ce = cudaGetLastError();
     cudaFreeAsync(base, st);
     if (ce != cudaSuccess) {
