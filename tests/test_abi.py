@@ -52,3 +52,25 @@ def test_no_cpu_backend_behind_the_product(lib):
     # device "CPU" must be refused: no CPU fallback (north_star)
     d = pkg.bindings.Device.new("CPU", 0)
     assert lib.dll.icicle_set_device(C.byref(d)) == 1  # INVALID_DEVICE
+
+
+def test_header_is_plain_c_and_links(tmp_path):
+    """include/icicle_b200.h is what a cgo / JNI / Rust-bindgen consumer sees: it must compile as C99 (and C++11) on its
+    own, and a C program using it must link against the library and get the documented struct sizes."""
+    import subprocess
+    src = tmp_path / "consumer.c"
+    src.write_text(
+        '#include <stdio.h>\n#include "icicle_b200.h"\n'
+        "int main(void) {\n"
+        "  printf(\"%zu %zu %zu %zu %zu %s\\n\", sizeof(MSMConfig), sizeof(NTTConfig), sizeof(VecOpsConfig),\n"
+        "         sizeof(b200_groth16_proof), sizeof(bn254_fq12_t), b200_version());\n"
+        "  bn254_scalar_t a = {{5}}, b = {{7}}, c;\n  bn254_mul(&a, &b, &c);\n  return c.limbs[0] == 35 ? 0 : 1;\n}\n")
+    inc = os.path.join(ROOT, "include")
+    libdir = os.path.dirname(pkg.LIB_PATH)
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", inc, "-fsyntax-only", str(src)], check=True)
+    subprocess.run(["g++", "-std=c++11", "-Wall", "-I", inc, "-fsyntax-only", "-x", "c++", str(src)], check=True)
+    exe = tmp_path / "consumer"
+    subprocess.run(["gcc", "-std=c99", "-I", inc, str(src), "-o", str(exe), "-L", libdir, "-licicle_b200",
+                    f"-Wl,-rpath,{libdir}"], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()
+    assert out[:5] == ["40", "64", "32", "256", "384"] and "sm_100a" in out
