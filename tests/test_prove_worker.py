@@ -53,3 +53,24 @@ def test_worker_proves_golden_instance(tmp_path):
     # prove -> verify in one worker session, on the files the worker itself wrote
     r = run(cmd + f"verify --proof {proof} --public {public} --vk {base}.vk.json\nexit\n", env=env)
     assert r.returncode == 0 and r.stdout.count("COMMAND_COMPLETED") == 3 and "COMMAND_FAILED" not in r.stdout
+
+
+def test_example_client_speaks_the_protocol():
+    """examples/worker_client.py (the counterpart of the reference's examples/python/main.py) against the real worker:
+    a verify-only session needs no GPU."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("worker_client", os.path.join(os.path.dirname(GOLD), "..", "examples", "worker_client.py"))
+    wc = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(wc)
+    if not os.path.exists(BIN):
+        pkg.build()
+    w = wc.Worker()
+    try:
+        base = os.path.join(GOLD, "complex_100")
+        _, lines, failed = w.run(f"verify --proof {base}.proof_rs.json --public {base}.public.json --vk {base}.vk.json")
+        assert not failed and lines[-1].endswith("COMMAND_COMPLETED")
+        _, lines, failed = w.run(f"verify --proof {GOLD}/complex_6.proof_rs.json --public {base}.public.json --vk {base}.vk.json")
+        assert failed
+    finally:
+        w.close()
+    assert w.proc.returncode == 0
