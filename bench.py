@@ -298,6 +298,19 @@ def main():
                      "frac": alg_mac / (acc * 1e-3) / imad_peak,
                      "note": "binding resource: 32-bit integer multiply-add pipe (IMAD.WIDE), peak measured in this run"},
     }
+    try:
+        # the practical ceiling of that pipe for this arithmetic: dependent 8x32-bit CIOS Montgomery products (the carry-in
+        # form of IMAD.WIDE occupies the pipe ~2.5x longer than the independent one), measured now on this GPU
+        mul_peak = lib.dll.b200_pipe_peak(6)
+        if mul_peak > 0:
+            mults = n_msm * windows * 10 / (acc * 1e-3)
+            roofline["field_mul"] = {"achieved_gmul_s": mults / 1e9, "peak_gmul_s": mul_peak / 1e9, "frac": mults / mul_peak,
+                                     "pipe_active_ncu": 0.895,
+                                     "note": "254-bit Montgomery products/s vs the multiplier microbenchmark (b200_pipe_peak(6)); "
+                                             "pipe_active_ncu = sm__pipe_fmaheavy_cycles_active of this kernel in "
+                                             "profiles/r01_ncu_msm_accumulate_g1_3200k.md"}
+    except Exception as exc:  # the extra view must never cost the bench line
+        log(f"field_mul roofline view skipped: {exc}")
     # secondary headline: standalone G1 MSM throughput with resident inputs
     t_ms = []
     for i in range(5):
