@@ -40,6 +40,25 @@ def lib() -> IcicleLib:
         _lib = IcicleLib(LIB_PATH)
     return _lib
 
+_tools = None
+
+
+def tools_lib():
+    """lib/libicicle_b200_tools.so: pipe probes, multiplier microbenchmarks and host models (research/); used by
+    bench.py for the measured integer-pipe peak and by the tests of the models - never by the product path."""
+    global _tools
+    if _tools is None:
+        import ctypes as C
+        path = os.path.join(PKG_DIR, "lib", "libicicle_b200_tools.so")
+        if not os.path.exists(path):
+            raise FileNotFoundError(f"{path} is missing: build it first (make -C {PKG_DIR})")
+        _tools = C.CDLL(path)
+        for name in ("b200_probe_cycles", "b200_imad_wide_peak", "b200_pipe_peak"):
+            getattr(_tools, name).restype = C.c_double
+        _tools.b200_probe_name.restype = C.c_char_p
+    return _tools
+
+
 from .prover import (CacheManager, ZKeyCache, groth16_prove, groth16_verify, groth16_verify_points,  # noqa: E402,F401
                      proof_json, proof_to_dict)
 from . import multi_gpu  # noqa: E402,F401

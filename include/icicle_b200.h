@@ -342,22 +342,11 @@ eIcicleError b200_groth16_verify_files(const char* proof_path, const char* publi
  * The reference generates its benchmark zkeys with snarkjs (scripts/setup.sh), which is unavailable offline. */
 eIcicleError b200_fixed_base_mul(const bn254_scalar_t* k, uint64_t n, int g2, int out_montgomery, void* out);
 
-/* Measured arithmetic-pipe peaks (operations/s) for the roofline: mode 0 IMAD, 1 IMAD.WIDE, 2 IMAD.HI, 3 DFMA,
- * 4 IMAD.WIDE+DFMA co-issue, 5 carry-chained wide multiply-adds. b200_imad_peak(wide) = mode 5 / mode 0. */
-double b200_pipe_peak(int mode);
-double b200_imad_peak(int wide);
 /* The Pippenger plan derived for an MSM shape (host-only; same code path as bn254_msm and the ZKeyCache):
  * out8 = {c, windows, factor, sets, buckets per set, buckets, work-item cap, n}; hconst9 (optional) = the 288-bit
  * signed-digit recoding constant sum_w 2^(c-1) 2^(c w). c = 0 asks for the heuristic (the reference's is
  * backend/cuda/src/msm/cuda_msm.cuh:45-48). */
 eIcicleError b200_msm_plan_info(int n, int c, int bitsize, int precompute_factor, int g2, int32_t* out8, uint32_t* hconst9);
-/* HOST model of bucket accumulation by batched affine addition (csrc/batch_affine_model.cu; DESIGN.md section 8.1, the
- * round-2 arithmetic item): pairwise-tree rounds with a two-level Montgomery trick, executed with the same per-thread
- * bodies (csrc/batch_affine.cuh) the experimental kernels wrap, checked against the XYZZ accumulation the MSM uses today.
- * max_rounds < 0: run to completion; otherwise stop after that many rounds and sum the leftovers serially. Returns the
- * number of mismatching buckets (0 = agreement; -1 = bad arguments); *products_per_add = field products per real
- * addition. Test infrastructure for the next kernel generation. */
-int b200_batch_affine_selfcheck(int g2, int n_entries, int n_buckets, int max_rounds, unsigned seed, double* products_per_add);
 /* kernel launches issued by this library since load (bench.py's gpu_launches) */
 unsigned long long b200_launch_count(void);
 /* CUDA-event timing of the MSM bucket-accumulation kernel (the dominant kernel) for bench.py's roofline:

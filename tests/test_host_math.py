@@ -91,13 +91,14 @@ def test_python_oracle_agrees_with_host_helpers(lib, rng):
 
 @pytest.mark.parametrize("g2", [0, 1])
 def test_batched_affine_bucket_model_matches_xyzz_accumulation(lib, g2):
-    """csrc/batch_affine.cuh + batch_affine_model.cu (DESIGN.md section 8.1, next kernel generation): pairwise-tree rounds
+    """csrc/batch_affine.cuh + research/batch_affine_model.cu (DESIGN.md section 8.1, next kernel generation): pairwise-tree rounds
     with a two-level Montgomery trick - executed with the very per-thread bodies the experimental kernels wrap -
     reproduce the bucket sums of today's XYZZ accumulation on data with repeated points (tangent case), opposite points
     (cancellation), identities, empty buckets and one giant bucket; with long buckets they spend 7.7-8.9 field products
     per addition on this adversarial data (true inversions included) where the XYZZ mixed add spends 10."""
     import ctypes as C
-    f = lib.dll.b200_batch_affine_selfcheck
+    import icicle_snark_b200 as pkg
+    f = pkg.tools_lib().b200_batch_affine_selfcheck
     for n, nb, rounds in ((0, 4, -1), (1, 1, -1), (2, 1, -1), (5000, 37, -1), (20000, 512, -1), (3000, 3, -1),
                           (4000, 64, 2), (9000, 1000, -1), (6000, 10, 0), (6000, 10, 1), (70000, 300, 5)):
         ppa = C.c_double(0)

@@ -1,15 +1,14 @@
-import ctypes as C, sys
+"""Integer-pipe probes of the GPU this runs on (research/pipes2.cu in lib/libicicle_b200_tools.so): cycles per
+warp-instruction per SM sub-partition for the instruction classes the field multiplier is built from, the resulting
+wide-MAC peak (the MSM/NTT roofline denominator) and the throughput of the production Montgomery product."""
+import sys
 sys.path.insert(0, ".")
 import __graft_entry__ as g
-pkg = g.load_package(); lib = pkg.lib(); lib.set_device("CUDA", 0)
-lib.dll.b200_pipe_peak.restype = C.c_double
-for m, name in enumerate(["imad.lo", "imad.wide", "imad.hi", "dfma", "wide+dfma mixed", "wide carry chain", "Fq mul 8x32 CIOS (G mul/s x1000)", "Fq mul 9x29 imm (G mul/s x1000)", "Fq mul 9x29 regs (G mul/s x1000)", "carry-save wide MAC (+counter)", "Fq mul FP64 6x48 alone (G mul/s x1000)", "CIOS + FP64 co-run, half the warps each (G mul/s x1000)"]):
-    print(f"{name:20s} {lib.dll.b200_pipe_peak(m)/1e12:8.3f} Tops/s")
-print("mul29 selfcheck mismatches:", lib.dll.b200_mul29_selfcheck())
-print("mul48 (FP64) selfcheck mismatches:", lib.dll.b200_mul48_selfcheck())
-for m, name in ((12, "Fq sqr dedicated (SOS)"), (13, "Fq mul wide + SOS reduce")):
-    print(f"{name:40s} {lib.dll.b200_pipe_peak(m)/1e9:8.1f} G/s")
-for ci, cf in ((4, 2),):
-    out = (C.c_double * 3)()
-    lib.dll.b200_corun_test(out, ci, cf)
-    print(f"co-residency {ci} int CTAs + {cf} fp64 CTAs per SM: int alone {out[0]/1e9:.1f}  fp64 alone {out[1]/1e9:.1f}  together {out[2]/1e9:.1f} G mul/s")
+pkg = g.load_package()
+pkg.lib().set_device("CUDA", 0)
+t = pkg.tools_lib()
+for k in range(t.b200_probe_count()):
+    i = t.b200_probe_id(k)
+    print(f"T{i:<3d} {t.b200_probe_name(k).decode():58s} {t.b200_probe_cycles(i):7.3f} cycles / warp-instruction / SMSP")
+print(f"IMAD.WIDE peak {t.b200_imad_wide_peak() / 1e12:.2f} T wide MAC/s")
+print(f"Fq Montgomery products (8x32 CIOS, dependent chains): {t.b200_pipe_peak(6) / 1e9:.1f} G/s")
