@@ -176,6 +176,7 @@ struct b200_zkey_cache {
   cudaEvent_t ev_start = nullptr, ev_h2d = nullptr, ev_r1cs = nullptr, ev_ntt = nullptr, ev_g1 = nullptr,
               ev_g2 = nullptr, ev_q = nullptr, ev_prev = nullptr, ev_b1 = nullptr;
   std::mutex mu;
+  bool in_flight = false; // commit_begin succeeded and holds `mu` until commit_end
 };
 
 namespace b200 {
@@ -428,6 +429,13 @@ namespace b200 {
     c->planC = c->planA;
     c->planB2 = c->planA; // same digits/windows as the G1 MSMs: B2 reuses their sort
     c->planH = plan_for(c->h_hi - c->h_lo, false);
+    {
+      // entries pack the sign in bit 31 of (point index * factor + table column); entry positions are 32-bit
+      const uint64_t f = (uint64_t)c->precompute;
+      if ((uint64_t)c->n_vars * f >= (1ull << 31) || (uint64_t)N * f >= (1ull << 31) || c->planA.entries() >= (1ull << 32) ||
+          c->planH.entries() >= (1ull << 32))
+        return fail(ICICLE_INVALID_ARGUMENT);
+    }
     if ((err = upload_points<Fq>(c, sec[5], 0, c->a_lo, c->a_hi, c->planA, &c->pA, st)) != ICICLE_SUCCESS) return fail(err);
     {
       // which signals of the shard have a B point at all? (B1 and B2 are zero together: same v_s(tau))
@@ -471,6 +479,8 @@ namespace b200 {
     uint32_t declared = 0;
     memcpy(&declared, cs.p, 4);
     c->n_coef = (cs.size - 4) / s_coef;
+    // 32-bit CSR positions / entry indices: refuse what would wrap instead of reading out of bounds
+    if (c->n_coef >= (1ull << 32) || declared != c->n_coef || (cs.size - 4) % s_coef != 0) return fail(ICICLE_INVALID_ARGUMENT);
     const uint8_t* rec = cs.p + 4;
     std::vector<uint32_t> row_ptr(2 * (size_t)N + 1, 0);
     for (uint64_t i = 0; i < c->n_coef; ++i) {
@@ -739,15 +749,15 @@ namespace b200 {
     G2XYZZ s_d2;
   };
 
-  static void compute_blind(const b200_zkey_cache* c, const bn254_scalar_t* r_in, const bn254_scalar_t* s_in, BlindTerms& b)
+  static eIcicleError compute_blind(const b200_zkey_cache* c, const bn254_scalar_t* r_in, const bn254_scalar_t* s_in, BlindTerms& b)
   {
     if (r_in && s_in) {
       memcpy(&b.r, r_in, 32);
       memcpy(&b.s, s_in, 32);
-    } else { // ScalarCfg::generate_random(2) (proof_helper.rs:276-278)
-      std::mt19937_64 rng(std::random_device{}());
-      b.r = host_random_fr(rng);
-      b.s = host_random_fr(rng);
+    } else {
+      // ScalarCfg::generate_random(2) (proof_helper.rs:276-278) - but from the kernel CSPRNG (the zero-knowledge
+      // property rests on r, s being unpredictable); a failed draw is an error, never a weaker generator
+      if (!host_secure_random_fr(b.r) || !host_secure_random_fr(b.s)) return ICICLE_UNKNOWN_FALLBACK;
     }
     G1XYZZ d1 = G1XYZZ::from_affine(c->delta1);
     G2XYZZ d2 = G2XYZZ::from_affine(c->delta2);
@@ -756,6 +766,7 @@ namespace b200 {
     b.s_d1 = host_scalar_mul(d1, b.s);
     b.rs_d1 = host_scalar_mul(d1, rs);
     b.s_d2 = host_scalar_mul(d2, b.s);
+    return ICICLE_SUCCESS;
   }
 
   static eIcicleError finish_with(
@@ -943,22 +954,43 @@ eIcicleError b200_groth16_commit_begin(
   if (!c || (poly_count > 0 && !out_dev)) return ICICLE_INVALID_POINTER;
   if (first_poly < 0 || poly_count < 0 || first_poly + poly_count > 3) return ICICLE_INVALID_ARGUMENT;
   c->mu.lock();
+  if (c->in_flight) { // (unreachable while `mu` is held by the pending pair; kept as a guard against misuse)
+    c->mu.unlock();
+    return ICICLE_INVALID_ARGUMENT;
+  }
   eIcicleError e = enqueue_upload(c, witness, n_witness, poly_count > 0);
   if (e == ICICLE_SUCCESS && poly_count > 0) e = enqueue_quotient_polys(c, first_poly, poly_count, (Fr*)out_dev);
   if (e == ICICLE_SUCCESS && poly_count == 0) cudaEventRecord(c->ev_r1cs, c->s_q); // keep the phase timers well-defined
   if (e == ICICLE_SUCCESS) e = enqueue_witness_msms(c); // keep the GPU busy while the caller exchanges slices
   if (e == ICICLE_SUCCESS && cudaStreamSynchronize(c->s_q) != cudaSuccess) e = ICICLE_SYNCHRONIZATION_FAILED;
-  if (e != ICICLE_SUCCESS) c->mu.unlock(); // otherwise held until commit_end
+  if (e != ICICLE_SUCCESS) {
+    cudaStreamSynchronize(c->s_copy); // leave no half-enqueued proof behind
+    cudaStreamSynchronize(c->s_g1);
+    cudaStreamSynchronize(c->s_g2);
+    cudaStreamSynchronize(c->s_q);
+    (void)cudaGetLastError();
+    c->mu.unlock();
+  } else {
+    c->in_flight = true; // `mu` stays held until commit_end
+  }
   return e;
 }
 
 eIcicleError b200_groth16_commit_end(
   b200_zkey_cache* c, const void* a_dev, const void* b_dev, const void* c_dev, b200_groth16_partials* out, b200_prove_timings* tm)
 {
-  if (!c || !a_dev || !b_dev || !c_dev || !out) return ICICLE_INVALID_POINTER;
-  eIcicleError e = enqueue_h(c, (const Fr*)a_dev, (const Fr*)b_dev, (const Fr*)c_dev);
+  if (!c) return ICICLE_INVALID_POINTER;
+  if (!c->in_flight) return ICICLE_INVALID_ARGUMENT; // no successful commit_begin is pending on this cache
+  eIcicleError e = (!a_dev || !b_dev || !c_dev || !out) ? ICICLE_INVALID_POINTER : ICICLE_SUCCESS;
+  if (e == ICICLE_SUCCESS) e = enqueue_h(c, (const Fr*)a_dev, (const Fr*)b_dev, (const Fr*)c_dev);
   if (e == ICICLE_SUCCESS) e = enqueue_join(c);
   if (e == ICICLE_SUCCESS) e = commit_wait(c, out, tm);
+  if (e != ICICLE_SUCCESS) { // drain whatever commit_begin enqueued so the next proof starts clean
+    for (cudaStream_t st : {c->s_copy, c->s_g1, c->s_g2, c->s_q})
+      cudaStreamSynchronize(st);
+    (void)cudaGetLastError();
+  }
+  c->in_flight = false;
   c->mu.unlock();
   return e;
 }
@@ -993,7 +1025,7 @@ eIcicleError b200_groth16_finish(
 {
   if (!cache) return ICICLE_INVALID_POINTER;
   BlindTerms bt;
-  compute_blind(cache, r, s, bt);
+  B200_TRY(compute_blind(cache, r, s, bt));
   return finish_with(cache, parts, n_parts, bt, proof);
 }
 
@@ -1007,8 +1039,9 @@ eIcicleError b200_groth16_prove(
   std::lock_guard<std::mutex> g(cache->mu);
   B200_TRY(commit_enqueue(cache, witness, n_witness));
   BlindTerms bt;
-  compute_blind(cache, r, s, bt); // host work overlapped with the GPU
-  B200_TRY(commit_wait(cache, &parts, tm));
+  eIcicleError be = compute_blind(cache, r, s, bt); // host work overlapped with the GPU
+  B200_TRY(commit_wait(cache, &parts, tm));       // (always drain the enqueued proof before returning)
+  B200_TRY(be);
   return finish_with(cache, &parts, 1, bt, proof);
 }
 
@@ -1060,7 +1093,11 @@ eIcicleError b200_groth16_prove_files(
   memcpy(&n_witness, sec[1].p + 36, 4);
   if (sec[2].size < (uint64_t)n_witness * 32) return ICICLE_INVALID_ARGUMENT;
   b200_groth16_proof proof;
-  const char* fixed = getenv("B200_NO_RANDOMNESS"); // the reference's `no-randomness` cargo feature: r = s = 1
+  // the reference's `no-randomness` cargo feature (r = s = 1: proofs are NOT zero-knowledge); honoured only for the
+  // exact value "1" and announced, so that a stray variable cannot silently disable blinding in production
+  const char* nr_env = getenv("B200_NO_RANDOMNESS");
+  const bool fixed = nr_env && strcmp(nr_env, "1") == 0;
+  if (fixed) fprintf(stderr, "[icicle_b200] WARNING: B200_NO_RANDOMNESS=1 - blinding disabled (r = s = 1), proofs are not zero-knowledge\n");
   bn254_scalar_t one;
   memset(&one, 0, sizeof one);
   one.limbs[0] = 1;

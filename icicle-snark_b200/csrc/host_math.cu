@@ -10,6 +10,8 @@
 #include "common.cuh"
 #include "curve.cuh"
 #include "host_math.h"
+#include <cerrno>
+#include <sys/random.h>
 
 namespace b200 {
 
@@ -23,8 +25,6 @@ namespace b200 {
     return (a.x * b.z == b.x * a.z) && (a.y * b.z == b.y * a.z);
   }
 
-  template <class F>
-  static F curve_b();
   template <>
   Fq curve_b<Fq>()
   {
@@ -74,6 +74,35 @@ namespace b200 {
     memcpy(g.y.c0.v, yr, 32);
     memcpy(g.y.c1.v, yi, 32);
     return {Fq2::to_mont(g.x), Fq2::to_mont(g.y)};
+  }
+
+  // Blinding factors must come from the kernel's CSPRNG: a 32-bit-seeded mt19937 (what the reference's
+  // ScalarCfg::generate_random amounts to) lets an attacker enumerate seeds and confirm a candidate witness from pi_a.
+  bool host_secure_random_fr(Fr& out)
+  {
+    for (int tries = 0; tries < 64; ++tries) {
+      Fr x;
+      size_t got = 0;
+      while (got < sizeof(x.v)) {
+        ssize_t r = getrandom(reinterpret_cast<uint8_t*>(x.v) + got, sizeof(x.v) - got, 0);
+        if (r < 0) {
+          if (errno == EINTR) continue;
+          return false;
+        }
+        got += (size_t)r;
+      }
+      x.v[7] &= 0x3fffffff; // rejection sampling on 254 bits: uniform in [0, r)
+      for (int i = 7; i >= 0; --i) {
+        if (x.v[i] != FrCfg::P(i)) {
+          if (x.v[i] < FrCfg::P(i)) {
+            out = x;
+            return true;
+          }
+          break;
+        }
+      }
+    }
+    return false;
   }
 
   Fr host_random_fr(std::mt19937_64& rng)

@@ -41,8 +41,17 @@ namespace b200 {
     return acc;
   }
 
+  // curve coefficient b (G1: 3, G2: 3/(9+u)) in Montgomery form; specialised in host_math.cu
+  template <class F>
+  F curve_b();
+  template <>
+  Fq curve_b<Fq>();
+  template <>
+  Fq2 curve_b<Fq2>();
+
   G1Affine g1_generator_mont();
   G2Affine g2_generator_mont();
-  Fr host_random_fr(std::mt19937_64& rng); // standard form, uniform in [0, r)
+  Fr host_random_fr(std::mt19937_64& rng); // standard form, uniform in [0, r): test-data generators only
+  bool host_secure_random_fr(Fr& out);     // getrandom(2) + rejection sampling; false if the kernel CSPRNG fails
 
 } // namespace b200

@@ -477,6 +477,25 @@ namespace b200 {
 
   // e(-A, B) * e(cpub, gamma_2) * e(C, delta_2) * e(alpha_1, beta_2) == 1, cpub = IC_0 + sum pub_i IC_{i+1}
   // (src/proof_helper.rs:319-372).  All inputs in STANDARD form, as the JSON files hold them.
+  // little-endian 8x32 value < modulus (P(k) = limb k)
+  template <class P>
+  static bool limbs_below(const uint32_t* v, P modulus)
+  {
+    for (int i = 7; i >= 0; --i) {
+      uint32_t m = modulus(i);
+      if (v[i] != m) return v[i] < m;
+    }
+    return false;
+  }
+
+  // y^2 == x^3 + b for a Montgomery-form affine point; (0,0) is the identity and passes
+  template <class F>
+  static bool affine_on_curve(const Affine<F>& p)
+  {
+    if (p.is_inf()) return true;
+    return p.y.sqr() == p.x.sqr() * p.x + curve_b<F>();
+  }
+
   static bool groth16_check(
     const G1Affine& a, const G2Affine& b, const G1Affine& c, const G1Affine& alpha1, const G2Affine& beta2, const G2Affine& gamma2,
     const G2Affine& delta2, const G1Affine* ic, const Fr* publics, size_t n_public)
@@ -585,6 +604,32 @@ EXPORT eIcicleError b200_groth16_verify(
 {
   if (!proof || !vk_alpha_1 || !vk_beta_2 || !vk_gamma_2 || !vk_delta_2 || !ic || !valid || (n_public && !publics))
     return ICICLE_INVALID_POINTER;
+  // Input validation the reference's verifier (proof_helper.rs:319-372) does not do and snarkjs does: non-canonical
+  // public inputs alias (x and x + r verify alike), non-canonical coordinates are proof malleability, and the pairing
+  // is only sound for points on the curve / in the order-r subgroup of the twist.  Any violation: not valid.
+  *valid = 0;
+  for (uint64_t i = 0; i < n_public; ++i)
+    if (!limbs_below(publics[i].limbs, [](int k) { return FrCfg::P(k); })) return ICICLE_SUCCESS;
+  {
+    const G1Affine& a = *reinterpret_cast<const G1Affine*>(&proof->pi_a);
+    const G2Affine& b = *reinterpret_cast<const G2Affine*>(&proof->pi_b);
+    const G1Affine& c = *reinterpret_cast<const G1Affine*>(&proof->pi_c);
+    auto fq_ok = [](const Fq& x) { return limbs_below(x.v, [](int k) { return FqCfg::P(k); }); };
+    if (!fq_ok(a.x) || !fq_ok(a.y) || !fq_ok(c.x) || !fq_ok(c.y) || !fq_ok(b.x.c0) || !fq_ok(b.x.c1) || !fq_ok(b.y.c0) ||
+        !fq_ok(b.y.c1))
+      return ICICLE_SUCCESS;
+    if (!affine_on_curve(affine_to_mont(a)) || !affine_on_curve(affine_to_mont(c))) return ICICLE_SUCCESS;
+    G2Affine bm = affine_to_mont(b);
+    if (!affine_on_curve(bm)) return ICICLE_SUCCESS;
+    // subgroup check on the twist: [r]B == O  (G1 has cofactor 1)
+    Fr r_minus_1;
+    for (int k = 0; k < 8; ++k)
+      r_minus_1.v[k] = FrCfg::P(k);
+    r_minus_1.v[0] -= 1; // r is odd
+    XYZZ<Fq2> t = host_scalar_mul(XYZZ<Fq2>::from_affine(bm), r_minus_1);
+    t.madd(bm);
+    if (!t.is_inf()) return ICICLE_SUCCESS;
+  }
   *valid = groth16_check(
              *reinterpret_cast<const G1Affine*>(&proof->pi_a), *reinterpret_cast<const G2Affine*>(&proof->pi_b),
              *reinterpret_cast<const G1Affine*>(&proof->pi_c), *reinterpret_cast<const G1Affine*>(vk_alpha_1),
@@ -624,9 +669,10 @@ EXPORT eIcicleError b200_groth16_verify_files(const char* proof_path, const char
   const Value* npv = vk.get("nPublic");
   if (!icv || icv->kind != Value::Array || !npv || npv->kind != Value::Number || pub.kind != Value::Array) return ICICLE_INVALID_ARGUMENT;
   size_t n_public = (size_t)strtoull(npv->text.c_str(), nullptr, 10);
-  // `public.iter().take(n_public)`: extra public values are ignored, IC must cover the ones used
-  size_t used = pub.items.size() < n_public ? pub.items.size() : n_public;
-  if (icv->items.size() < used + 1) return ICICLE_INVALID_ARGUMENT;
+  // The reference takes `public.iter().take(n_public)` and zips it with IC, so a short public.json silently proves a
+  // statement with the missing inputs read as 0 and a long one is truncated.  Here the three counts must agree.
+  if (pub.items.size() != n_public || icv->items.size() != n_public + 1) return ICICLE_INVALID_ARGUMENT;
+  size_t used = n_public;
   std::vector<G1Affine> ic(used + 1);
   for (size_t i = 0; i <= used; ++i)
     if (!g1_of(&icv->items[i], ic[i])) return ICICLE_INVALID_ARGUMENT;

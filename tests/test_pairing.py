@@ -126,13 +126,100 @@ def test_verify_files_mirror(lib, tmp_path):
     trailing.write_text(open(base + ".proof_r1s1.json").read() + " x")
     with pytest.raises(pkg.IcicleError):
         pkg.groth16_verify(str(trailing), base + ".public.json", base + ".vk.json", lib=lib)
-    # extra public values are ignored (`public.iter().take(n_public)`), as is snarkjs's vk_alphabeta_12
-    extra = tmp_path / "public_extra.json"
-    extra.write_text(json.dumps(json.load(open(base + ".public.json")) + ["5"]))
+    # snarkjs's vk_alphabeta_12 is ignored; the number of public values must equal nPublic and IC must hold nPublic + 1
+    # points (the reference's `public.iter().take(n_public)` zip would read missing inputs as absent terms)
     d = json.load(open(base + ".vk.json"))
     d["vk_alphabeta_12"] = [[["1", "2"], ["3", "4"], ["5", "6"]], [["7", "8"], ["9", "10"], ["11", "12"]]]
     vk2 = tmp_path / "vk_snarkjs.json"
     vk2.write_text(json.dumps(d, indent=1))
-    pkg.groth16_verify(base + ".proof_r1s1.json", str(extra), str(vk2), lib=lib)
+    pkg.groth16_verify(base + ".proof_r1s1.json", base + ".public.json", str(vk2), lib=lib)
+    extra = tmp_path / "public_extra.json"
+    extra.write_text(json.dumps(json.load(open(base + ".public.json")) + ["5"]))
+    short = tmp_path / "public_short.json"
+    short.write_text("[]")
+    for bad_pub in (extra, short):
+        with pytest.raises(pkg.IcicleError):
+            pkg.groth16_verify(base + ".proof_r1s1.json", str(bad_pub), str(vk2), lib=lib)
+    d2 = dict(d, IC=d["IC"] + [d["IC"][0]])
+    vk3 = tmp_path / "vk_long_ic.json"
+    vk3.write_text(json.dumps(d2))
+    with pytest.raises(pkg.IcicleError):
+        pkg.groth16_verify(base + ".proof_r1s1.json", base + ".public.json", str(vk3), lib=lib)
     ok = C.c_int(7)
     assert lib.dll.b200_groth16_verify_files(None, None, None, C.byref(ok)) == pkg.ERRORS.index("INVALID_POINTER")
+
+
+R_MOD = 0x30644E72E131A029B85045B68181585D2833E84879B9709143E1F593F0000001
+
+
+def test_verifier_rejects_non_canonical_and_off_curve_inputs(lib):
+    """Aliased public inputs (x + r), non-canonical coordinates (x + q), points off the curve and G2 points outside
+    the order-r subgroup must not verify (snarkjs rejects them; the reference's verifier does not look)."""
+    n = 6
+    vk = load_vk(n)
+    base = os.path.join(GOLD, f"complex_{n}")
+    public = [int(x) for x in json.load(open(base + ".public.json"))]
+    good = proof_points(base + ".proof_rs.json")
+    assert pkg.groth16_verify_points(lib, good, public, vk)
+    words = lambda v: np.frombuffer(int(v).to_bytes(32, "little"), dtype=np.uint32).copy()
+    val = lambda w: int.from_bytes(np.ascontiguousarray(w, dtype=np.uint32).tobytes(), "little")
+    # public input aliasing: public[0] + r is the same field element
+    assert public[0] + R_MOD < 1 << 256
+    assert not pkg.groth16_verify_points(lib, good, [public[0] + R_MOD] + public[1:], vk)
+    # coordinate malleability: pi_a.x + q
+    bad = {k: v.copy() for k, v in good.items()}
+    bad["pi_a"][:8] = words(val(good["pi_a"][:8]) + P_MOD)
+    assert not pkg.groth16_verify_points(lib, bad, public, vk)
+    bad = {k: v.copy() for k, v in good.items()}
+    bad["pi_b"][8:16] = words(val(good["pi_b"][8:16]) + P_MOD)
+    assert not pkg.groth16_verify_points(lib, bad, public, vk)
+    # off the curve: y + 1
+    for name, off in (("pi_a", 8), ("pi_c", 8), ("pi_b", 16)):
+        bad = {k: v.copy() for k, v in good.items()}
+        bad[name][off:off + 8] = words((val(good[name][off:off + 8]) + 1) % P_MOD)
+        assert not pkg.groth16_verify_points(lib, bad, public, vk)
+    # on the twist but outside the order-r subgroup (the twist's cofactor is > 1, so almost every twist point is)
+    from oracle import bn254_py as O
+    Q = O.Q_MOD
+
+    def fq2_sqrt(a):  # q = 3 mod 4
+        if a.is_zero():
+            return a
+        norm = (a.c0 * a.c0 + a.c1 * a.c1) % Q
+        alpha = pow(norm, (Q + 1) // 4, Q)
+        if alpha * alpha % Q != norm:
+            return None
+        for sgn in (1, -1):
+            delta = (a.c0 + sgn * alpha) * pow(2, -1, Q) % Q
+            x0 = pow(delta, (Q + 1) // 4, Q)
+            if x0 * x0 % Q == delta and x0:
+                r = O.Fq2(x0, a.c1 * pow(2 * x0, -1, Q))
+                if r * r == a:
+                    return r
+        return None
+
+    def mul_no_reduce(P, k):
+        acc = None
+        while k:
+            if k & 1:
+                acc = O.G2.add(acc, P)
+            P = O.G2.add(P, P)
+            k >>= 1
+        return acc
+
+    found = None
+    for x0 in range(1, 50):
+        x = O.Fq2(x0, 1)
+        y = fq2_sqrt(x * x * x + O.G2.b)
+        if y is not None and O.G2.is_on_curve((x, y)) and mul_no_reduce((x, y), R_MOD) is not None:
+            found = (x, y)
+            break
+    assert found is not None
+    assert mul_no_reduce(O.G2.gen, R_MOD) is None  # sanity of the helper: the generator has order r
+    bad = {k: v.copy() for k, v in good.items()}
+    bad["pi_b"] = np.concatenate([words(found[0].c0), words(found[0].c1), words(found[1].c0), words(found[1].c1)])
+    assert not pkg.groth16_verify_points(lib, bad, public, vk)
+    # ... while a genuine subgroup point in pi_b's place passes the input checks and only fails the pairing equation
+    g2w = np.array(O.g2_affine_to_words(O.G2.gen), dtype=np.uint32)
+    bad["pi_b"] = g2w
+    assert not pkg.groth16_verify_points(lib, bad, public, vk)
