@@ -93,7 +93,16 @@ namespace b200 {
 
   // kernel launches issued by this library since load (bench.py's gpu_launches claim)
   extern unsigned long long g_launches;
-  // optional CUDA events recorded around the accumulate kernel of the next MSM (b200_profile_accumulate)
-  extern cudaEvent_t g_profile_events[2];
+  // Profiling mode (b200_profile_accumulate / b200_profile_records; bench.py's roofline): while enabled, the bucket-
+  // accumulation phase of every MSM is isolated by device-wide synchronisation on both sides and timed with CUDA events
+  // on its own stream, so each record is the duration of that launch running ALONE (the proof's streams otherwise
+  // overlap it with other kernels).  Off by default; never enabled inside a timed region.
+  struct MsmProfileRec {
+    int g2, nsel, n, windows, c, factor, nbuckets, batched; // batched: rounds of batched-affine accumulation (0 = XYZZ)
+    float ms;
+  };
+  extern int g_profile_mode;
+  void msm_profile_begin(cudaStream_t st);
+  void msm_profile_end(cudaStream_t st, const MsmPlan& plan, int g2, int nsel, int batched);
 
 } // namespace b200

@@ -1,11 +1,39 @@
 // BN254 G1 MSM instantiation + plan selection + the bn254_msm / bn254_msm_precompute_bases symbols
 // (/root/reference/icicle/src/msm.cpp:12-16,45-49).
+#include <cstring>
+#include <mutex>
+#include <vector>
+
 #include "msm_impl.cuh"
 
 namespace b200 {
 
   unsigned long long g_launches = 0;
-  cudaEvent_t g_profile_events[2] = {nullptr, nullptr};
+  int g_profile_mode = 0;
+  static cudaEvent_t g_profile_events[2] = {nullptr, nullptr};
+  static std::vector<MsmProfileRec> g_profile_recs;
+  static std::mutex g_profile_mu;
+
+  void msm_profile_begin(cudaStream_t st)
+  {
+    if (!g_profile_mode) return;
+    cudaDeviceSynchronize();
+    if (!g_profile_events[0]) {
+      cudaEventCreate(&g_profile_events[0]);
+      cudaEventCreate(&g_profile_events[1]);
+    }
+    cudaEventRecord(g_profile_events[0], st);
+  }
+  void msm_profile_end(cudaStream_t st, const MsmPlan& plan, int g2, int nsel, int batched)
+  {
+    if (!g_profile_mode || !g_profile_events[0]) return;
+    cudaEventRecord(g_profile_events[1], st);
+    cudaDeviceSynchronize();
+    float ms = -1.f;
+    cudaEventElapsedTime(&ms, g_profile_events[0], g_profile_events[1]);
+    std::lock_guard<std::mutex> g(g_profile_mu);
+    g_profile_recs.push_back({g2, nsel, plan.n, plan.windows, plan.c, plan.factor, plan.nbuckets, batched, ms});
+  }
 
   MsmPlan make_msm_plan(int n, int c_req, int bitsize, int factor, bool g2)
   {
@@ -106,23 +134,30 @@ eIcicleError bn254_msm_precompute_bases(
 
 unsigned long long b200_launch_count(void) { return g_launches; }
 
-// enable != 0: record CUDA events around the bucket-accumulation kernel of subsequent MSMs (single stream use);
-// enable == 0: stop. Returns the duration in ms of the last recorded accumulate launch, or -1.
+// enable != 0: profiling mode on (see msm.cuh: every MSM's bucket-accumulation phase runs isolated and is timed),
+// records cleared; enable == 0: off.  Returns the duration in ms of the last recorded accumulation phase, or -1.
 float b200_profile_accumulate(int enable)
 {
-  float ms = -1.f;
-  if (g_profile_events[0] && g_profile_events[1]) {
-    if (cudaEventSynchronize(g_profile_events[1]) == cudaSuccess) cudaEventElapsedTime(&ms, g_profile_events[0], g_profile_events[1]);
-  }
-  if (enable && !g_profile_events[0]) {
-    cudaEventCreate(&g_profile_events[0]);
-    cudaEventCreate(&g_profile_events[1]);
-  } else if (!enable && g_profile_events[0]) {
-    cudaEventDestroy(g_profile_events[0]);
-    cudaEventDestroy(g_profile_events[1]);
-    g_profile_events[0] = g_profile_events[1] = nullptr;
-  }
+  std::lock_guard<std::mutex> g(g_profile_mu);
+  float ms = g_profile_recs.empty() ? -1.f : g_profile_recs.back().ms;
+  if (enable && !g_profile_mode) g_profile_recs.clear();
+  g_profile_mode = enable ? 1 : 0;
   return ms;
+}
+
+// copies up to `cap` records {g2, nsel, n, windows, c, factor, nbuckets, batched_rounds, ms as float bits} (9 x 32-bit
+// words each) collected since profiling was enabled; returns the number of records available
+int b200_profile_records(int32_t* out9, int cap)
+{
+  std::lock_guard<std::mutex> g(g_profile_mu);
+  const int n = (int)g_profile_recs.size();
+  for (int i = 0; i < n && i < cap && out9; ++i) {
+    const MsmProfileRec& r = g_profile_recs[i];
+    const int32_t v[8] = {r.g2, r.nsel, r.n, r.windows, r.c, r.factor, r.nbuckets, r.batched};
+    memcpy(out9 + 9 * i, v, sizeof v);
+    memcpy(out9 + 9 * i + 8, &r.ms, 4);
+  }
+  return n;
 }
 
 } // extern "C"

@@ -373,7 +373,9 @@ namespace b200 {
     const int sms = sm_count();
     const unsigned ysel = (unsigned)nsel;
 
-    if (const int ba_rounds = batch_affine_rounds()) {
+    const int ba_rounds = batch_affine_rounds();
+    msm_profile_begin(st);
+    if (ba_rounds) {
       // experimental, off unless B200_BATCH_AFFINE is set: see msm_batch_affine.cuh
       eIcicleError be = msm_accumulate_batched_enqueue<F>(plan, sorted, sel, nsel, ba_rounds, buckets, st);
       if (be != ICICLE_SUCCESS) {
@@ -381,11 +383,9 @@ namespace b200 {
         return be;
       }
     } else {
-      if (g_profile_events[0]) cudaEventRecord(g_profile_events[0], st);
       B200_LAUNCH(
         msm_accumulate_kernel<F>, dim3(grid_for(max_items, 128, 16), ysel), 128, 0, st, sorted.sorted, total_items, sorted.entries,
         sel, buckets, partials, (uint32_t)nb, (uint32_t)max_items);
-      if (g_profile_events[1]) cudaEventRecord(g_profile_events[1], st);
       B200_LAUNCH(
         msm_fold_serial_kernel<F>, dim3(grid_for(nb, 128, 8), ysel), 128, 0, st, sorted.multi, sorted.multi_count, sorted.item_off,
         partials, buckets, (uint32_t)nb, (uint32_t)max_items);
@@ -393,6 +393,7 @@ namespace b200 {
         msm_fold_kernel<F>, dim3(sms, ysel), FOLD_BLOCK, FOLD_BLOCK * sizeof(XYZZ<F>), st, sorted.multi, sorted.multi_count,
         sorted.item_off, partials, buckets, (uint32_t)nb, (uint32_t)max_items);
     }
+    msm_profile_end(st, plan, sizeof(F) > sizeof(Fq) ? 1 : 0, nsel, ba_rounds);
     B200_LAUNCH(
       msm_reduce_chunks_kernel<F>, grid_for((size_t)nsets * chunks_per_set, 128, 16), 128, 0, st, pl, nsel, sorted.offsets, buckets,
       chunk_sums, chunk_runs, sum_stride);

@@ -349,9 +349,13 @@ eIcicleError b200_fixed_base_mul(const bn254_scalar_t* k, uint64_t n, int g2, in
 eIcicleError b200_msm_plan_info(int n, int c, int bitsize, int precompute_factor, int g2, int32_t* out8, uint32_t* hconst9);
 /* kernel launches issued by this library since load (bench.py's gpu_launches) */
 unsigned long long b200_launch_count(void);
-/* CUDA-event timing of the MSM bucket-accumulation kernel (the dominant kernel) for bench.py's roofline:
- * enable/disable recording; returns the last recorded launch's duration in ms (or -1). */
+/* Profiling mode for bench.py's roofline: while enabled, the bucket-accumulation phase (the dominant kernel) of every
+ * MSM - standalone or inside a proof - runs isolated (device-wide sync on both sides) and is timed with CUDA events.
+ * b200_profile_accumulate(enable) switches it (clearing old records when turning on) and returns the last recorded
+ * duration in ms (or -1); b200_profile_records copies the records collected so far, 9 32-bit words each:
+ * {g2, tables in the launch, n, windows, c, precompute factor, buckets, batched-affine rounds, float ms}. */
 float b200_profile_accumulate(int enable);
+int b200_profile_records(int32_t* out9, int cap);
 
 /* library identification: returns a static string "icicle-snark-b200 <version> sm_100a" */
 const char* b200_version(void);

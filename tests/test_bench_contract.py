@@ -34,5 +34,6 @@ def test_product_arm_json_line():
     assert d["value"] > 0 and d["e2e"]["value"] > 0 and d["e2e"]["h2d_bytes_per_step"] == 20002 * 32 and d["e2e"]["d2h_bytes_per_step"] == 576
     assert d["gpu_launches"] > 20 and d["higher_is_better"] is False and d["scaling"] == "strong" and d["n_gpus"] == 1
     rf = d["roofline"]
-    assert {"bound", "achieved", "peak", "unit", "frac", "traffic"} <= set(rf) and rf["bound"] == "hbm" and 0 < rf["frac"] < 1.5
+    assert {"bound", "achieved", "peak", "unit", "frac", "traffic"} <= set(rf) and rf["bound"] == "int_pipe" and 0 < rf["frac"] < 1.2 and 0 < rf["hbm"]["frac"] < 1.2
     assert {"sm_mhz", "sm_max_mhz", "reasons"} <= set(d["clocks"])
+    assert d["verified"]["ok"] is True and d["verified"]["library_pairing"] is True

@@ -42,6 +42,98 @@ def timed(fn, reps=5, warm=2, sync=None):
     return sorted(ts)[len(ts) // 2]
 
 
+def run(lib, pkg=pkg, msm=(16, 18, 20, 22, 24, 26), g2=(16, 18, 20, 22), ntt=(16, 18, 20, 22, 24), precompute=1, emit=None, log=None):
+    """Runs the sweeps on this rank's device; returns the list of result dicts (rank 0) and calls emit(dict) per point.
+    Under torch.distributed (initialised by the caller) the MSM is sharded, the NTT replicated."""
+    import torch.distributed as dist
+    world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+    rank = dist.get_rank() if world > 1 else 0
+    rng = np.random.default_rng(20261017)
+    results = []
+
+    def out(d):
+        if rank == 0:
+            results.append(d)
+            if emit:
+                emit(d)
+
+    def scalars(n):
+        s = rng.integers(0, 1 << 32, size=(n, 8), dtype=np.uint64).astype(np.uint32)
+        s[:, 7] %= 0x30644e72  # uniform below r up to the top limb
+        return s
+
+    def run_msm(lg, is_g2):
+        n = 1 << lg
+        n_loc = n // world
+        # points: k_i * G from the fixed-base tool (distinct, valid), Montgomery form, tiled above 2^22
+        m = min(n_loc, 1 << 22 if not is_g2 else 1 << 20)
+        base = synth.fixed_base(lib, scalars(m), g2=is_g2)
+        reps = (n_loc + m - 1) // m
+        pts = torch.from_numpy(base.view(np.int32)).cuda()
+        if reps > 1:
+            pts = pts.repeat(reps, 1)[:n_loc].contiguous()
+        sc = torch.from_numpy(scalars(n_loc).view(np.int32)).cuda()
+        res = torch.zeros(48 if is_g2 else 24, dtype=torch.int32, device="cuda")
+        cfg = B.MSMConfig.default()
+        cfg.are_scalars_on_device = cfg.are_points_on_device = cfg.are_results_on_device = True
+        cfg.are_points_montgomery_form = True
+        cfg.is_async = True
+        tab = pts
+        if precompute > 1:
+            cfg.precompute_factor = precompute
+            w = 32 if is_g2 else 16
+            tab = torch.empty((n_loc * precompute, w), dtype=torch.int32, device="cuda")
+            lib.msm_precompute_bases(pts.data_ptr(), cfg, g2=is_g2, n=n_loc, out=tab.data_ptr())
+            torch.cuda.synchronize()
+        gathered = [torch.empty_like(res) for _ in range(world)] if world > 1 else None
+
+        def step():
+            lib.msm(sc.data_ptr(), tab.data_ptr(), cfg, g2=is_g2, results=res.data_ptr(), msm_size=n_loc)
+            if world > 1:
+                dist.all_gather(gathered, res)
+
+        ms = timed(step, sync=(dist.barrier if world > 1 else None))
+        t = torch.tensor([ms], device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        info = (C.c_int32 * 8)()
+        lib.dll.b200_msm_plan_info(C.c_int(n_loc), C.c_int(0), C.c_int(254), C.c_int(precompute), C.c_int(int(is_g2)), info, None)
+        out({"op": "msm_g2" if is_g2 else "msm_g1", "log_n": lg, "n_gpus": world, "precompute": precompute, "c": int(info[0]),
+             "windows": int(info[1]), "ms": round(ms, 4), "mpoints_s": round(n / ms / 1e3, 2),
+             # wide multiply-adds per second over the bucket additions alone (SURVEY 8d unit: 10 / 30 products x 136 MACs)
+             "t_mac_s": round(n * int(info[1]) * (30 if is_g2 else 10) * 136 / ms / 1e9, 3)})
+        del pts, sc, tab
+
+    for lg in msm:
+        if log:
+            log(f"sweep: G1 MSM 2^{lg}")
+        run_msm(lg, False)
+    for lg in g2:
+        if log:
+            log(f"sweep: G2 MSM 2^{lg}")
+        run_msm(lg, True)
+    ntt = list(ntt)
+    if ntt:
+        lib.ntt_release_domain()
+        lib.ntt_init_domain(lib.get_root_of_unity(1 << max(ntt)))
+    for lg in ntt:
+        n, batch = 1 << lg, 3
+        x = torch.from_numpy(scalars(n * batch).view(np.int32)).cuda()
+        y = torch.empty_like(x)
+        cfg = B.NTTConfig.default()
+        cfg.batch_size = batch
+        cfg.are_inputs_on_device = cfg.are_outputs_on_device = True
+        cfg.is_async = True
+        ms = timed(lambda: lib.ntt(x.data_ptr(), B.kForward, cfg, out=y.data_ptr(), size=n))
+        muls = batch * n * (lg / 2 + (-(-lg // 8) - 1))
+        out({"op": "ntt_fr_fwd_batch3", "log_n": lg, "n_gpus": world, "replicas": world, "ms": round(ms, 4),
+             "melem_s": round(batch * n / ms / 1e3, 1), "algorithmic_gb_s": round(batch * n * 64 / ms / 1e6, 1),
+             "field_mul_g_s": round(muls / ms / 1e6, 1), "t_mac_s": round(muls * 136 / ms / 1e9, 3)})
+        del x, y
+    return results
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--msm", default="16,18,20,22,24,26")
@@ -56,74 +148,8 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     lib = pkg.lib()
     lib.set_device("CUDA", local)
-    rng = np.random.default_rng(20261017)
-
-    def scalars(n):
-        s = rng.integers(0, 1 << 32, size=(n, 8), dtype=np.uint64).astype(np.uint32)
-        s[:, 7] %= 0x30644e72  # uniform below r up to the top limb
-        return s
-
-    def run_msm(lg, g2):
-        n = 1 << lg
-        n_loc = n // world
-        # points: k_i * G from the fixed-base tool (distinct, valid), Montgomery form, tiled above 2^22
-        m = min(n_loc, 1 << 22 if not g2 else 1 << 20)
-        base = synth.fixed_base(lib, scalars(m), g2=g2)
-        reps = (n_loc + m - 1) // m
-        pts = torch.from_numpy(base.view(np.int32)).cuda()
-        if reps > 1:
-            pts = pts.repeat(reps, 1)[:n_loc].contiguous()
-        sc = torch.from_numpy(scalars(n_loc).view(np.int32)).cuda()
-        res = torch.zeros(48 if g2 else 24, dtype=torch.int32, device="cuda")
-        cfg = B.MSMConfig.default()
-        cfg.are_scalars_on_device = cfg.are_points_on_device = cfg.are_results_on_device = True
-        cfg.are_points_montgomery_form = True
-        cfg.is_async = True
-        tab = pts
-        if args.precompute > 1:
-            cfg.precompute_factor = args.precompute
-            w = 32 if g2 else 16
-            tab = torch.empty((n_loc * args.precompute, w), dtype=torch.int32, device="cuda")
-            lib.msm_precompute_bases(pts.data_ptr(), cfg, g2=g2, n=n_loc, out=tab.data_ptr())
-            torch.cuda.synchronize()
-
-        def step():
-            lib.msm(sc.data_ptr(), tab.data_ptr(), cfg, g2=g2, results=res.data_ptr(), msm_size=n_loc)
-            if world > 1:
-                out = [torch.empty_like(res) for _ in range(world)]
-                dist.all_gather(out, res)
-
-        ms = timed(step, sync=(dist.barrier if world > 1 else None))
-        t = torch.tensor([ms], device="cuda")
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        if rank == 0:
-            print(json.dumps({"op": "msm_g2" if g2 else "msm_g1", "log_n": lg, "n_gpus": world, "precompute": args.precompute,
-                              "ms": round(float(t.item()), 4), "mpoints_s": round(n / float(t.item()) / 1e3, 2)}), flush=True)
-        del pts, sc, tab
-
-    for lg in [int(x) for x in args.msm.split(",") if x]:
-        run_msm(lg, False)
-    for lg in [int(x) for x in args.g2.split(",") if x]:
-        run_msm(lg, True)
-    ntt_logs = [int(x) for x in args.ntt.split(",") if x]
-    if ntt_logs:
-        lib.ntt_release_domain()
-        lib.ntt_init_domain(lib.get_root_of_unity(1 << max(ntt_logs)))
-    for lg in ntt_logs:
-        n, batch = 1 << lg, 3
-        x = torch.from_numpy(scalars(n * batch).view(np.int32)).cuda()
-        y = torch.empty_like(x)
-        cfg = B.NTTConfig.default()
-        cfg.batch_size = batch
-        cfg.are_inputs_on_device = cfg.are_outputs_on_device = True
-        cfg.is_async = True
-        ms = timed(lambda: lib.ntt(x.data_ptr(), B.kForward, cfg, out=y.data_ptr(), size=n))
-        muls = batch * n * (lg / 2 + (-(-lg // 8) - 1))
-        if rank == 0:
-            print(json.dumps({"op": "ntt_fr_fwd_batch3", "log_n": lg, "n_gpus": world, "replicas": world, "ms": round(ms, 4),
-                              "melem_s": round(batch * n / ms / 1e3, 1), "algorithmic_gb_s": round(batch * n * 64 / ms / 1e6, 1),
-                              "field_mul_g_s": round(muls / ms / 1e6, 1)}), flush=True)
+    ints = lambda s: [int(x) for x in s.split(",") if x]
+    run(lib, pkg, ints(args.msm), ints(args.g2), ints(args.ntt), args.precompute, emit=lambda d: print(json.dumps(d), flush=True))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -280,3 +280,28 @@ def vk_json(vk) -> str:
     return json.dumps({"protocol": "groth16", "curve": "bn128", "nPublic": int(vk["n_public"]),
                        "vk_alpha_1": g1(vk["alpha1"]), "vk_beta_2": g2(vk["beta2"]), "vk_gamma_2": g2(vk["gamma2"]),
                        "vk_delta_2": g2(vk["delta2"]), "IC": [g1(p) for p in vk["ic"]]}, indent=1)
+
+
+if __name__ == "__main__":
+    # python tools/synth.py --constraints N [--out DIR]: generate ComplexCircuit(N, N) with the product library on cuda:0
+    # and leave circuit.zkey / witness.wtns / vk.npz / verification_key.json in bench.py's instance cache (used by
+    # `bench.py --impl reference`, whose own process never loads the product library).
+    import argparse
+    import os
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root)
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--constraints", type=int, required=True)
+    ap.add_argument("--out", default=None)
+    a = ap.parse_args()
+    import __graft_entry__ as ge
+    import bench
+    if a.out:
+        bench.INSTANCE_DIR = os.path.dirname(os.path.abspath(a.out))
+    pkg = ge.load_package()
+    lib = pkg.lib()
+    lib.set_device("CUDA", 0)
+    bench.save_instance(a.constraints, *make_complex_circuit(lib, a.constraints))
+    print("instance written to", bench.instance_paths(a.constraints)[0])
