@@ -423,7 +423,9 @@ namespace b200 {
     const char* c_env = getenv("B200_MSM_C"); // tuning knob: window width of the cache's MSM plans (0/unset = heuristic)
     const int c_req = c_env ? atoi(c_env) : 0;
     auto plan_for = [&](uint32_t n, bool g2) {
-      return make_msm_plan(n ? (int)n : 1, c_req > 0 ? c_req : 0, 254, c->precompute, g2);
+      MsmPlan p = make_msm_plan(n ? (int)n : 1, c_req > 0 ? c_req : 0, 254, c->precompute, g2);
+      p.stride = p.factor; // the cache builds its own tables: only the multiples the plan uses
+      return p;
     };
     c->planA = plan_for(c->a_hi - c->a_lo, false);
     c->planC = c->planA;

@@ -31,7 +31,8 @@ namespace b200 {
     int n;        // scalars
     int c;        // window bits
     int windows;  // digits per scalar: ceil((bitsize+2)/c)
-    int factor;   // precompute factor f
+    int factor;   // precomputed multiples used per point: min(f, windows)
+    int stride;   // table stride: entry (i, j) of the base table is bases[i * stride + j] (the caller's f)
     int sets;     // bucket sets after precompute folding: ceil(windows/f)
     int bpw;      // buckets per set: 2^(c-1)
     int nbuckets; // sets * bpw
@@ -43,7 +44,7 @@ namespace b200 {
   MsmPlan make_msm_plan(int n, int c_req, int bitsize, int factor, bool g2);
 
   struct MsmDev { // plan fields the kernels need, passed by value
-    int n, c, windows, factor, sets, bpw, nbuckets, item_cap;
+    int n, c, windows, factor, stride, sets, bpw, nbuckets, item_cap;
     uint32_t h[9];
   };
   MsmDev msm_dev_plan(const MsmPlan& plan);

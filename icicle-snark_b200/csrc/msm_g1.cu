@@ -79,6 +79,7 @@ namespace b200 {
     p.c = c;
     p.windows = (bitsize + 2 + c - 1) / c;
     p.factor = factor < 1 ? 1 : factor;
+    p.stride = p.factor; // the table keeps the caller's layout out[i*f + j] even when fewer multiples are used
     if (p.factor > p.windows) p.factor = p.windows;
     p.sets = (p.windows + p.factor - 1) / p.factor;
     p.bpw = 1 << (c - 1);

@@ -373,10 +373,10 @@ namespace b200 {
     const int sms = sm_count();
     const unsigned ysel = (unsigned)nsel;
 
-    const int ba_rounds = batch_affine_rounds();
+    const int ba_rounds = msm_batch_affine_rounds(plan, sizeof(F) > sizeof(Fq));
     msm_profile_begin(st);
     if (ba_rounds) {
-      // experimental, off unless B200_BATCH_AFFINE is set: see msm_batch_affine.cuh
+      // long buckets: pairwise tree of batched affine additions (msm_batch_affine.cuh), 6-7 products per add
       eIcicleError be = msm_accumulate_batched_enqueue<F>(plan, sorted, sel, nsel, ba_rounds, buckets, st);
       if (be != ICICLE_SUCCESS) {
         cudaFreeAsync(base, st);

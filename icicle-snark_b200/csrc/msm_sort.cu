@@ -185,7 +185,7 @@ namespace b200 {
       base = __shfl_sync(0xffffffffu, base, leader);
       if (key != DIGIT_NONE) {
         uint32_t pos = base + __popc(peers & ((1u << lane) - 1));
-        entries[pos] = (uint32_t)(i * pl.factor + w / pl.sets) | (d & 0x80000000u);
+        entries[pos] = (uint32_t)(i * pl.stride + w / pl.sets) | (d & 0x80000000u);
       }
     }
   }
@@ -247,6 +247,7 @@ namespace b200 {
     pl.c = plan.c;
     pl.windows = plan.windows;
     pl.factor = plan.factor;
+    pl.stride = plan.stride;
     pl.sets = plan.sets;
     pl.bpw = plan.bpw;
     pl.nbuckets = plan.nbuckets;

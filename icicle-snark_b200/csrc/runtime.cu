@@ -6,6 +6,7 @@
 #include <map>
 #include <string>
 
+#include <cstdlib>
 #include "common.cuh"
 
 namespace b200 {

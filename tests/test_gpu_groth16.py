@@ -152,6 +152,43 @@ def test_msm_known_dlog_at_scale(gpu, rng):
     assert np.array_equal(gpu.to_affine(got), gpu.to_affine(want))
 
 
+def test_msm_known_dlog_with_precompute_tables_at_bench_plan(gpu, rng):
+    """The plan the bench's proof runs - precompute factor 16, c = 20, 13 windows, one bucket set - at 2^22 points, for
+    G1 and (2^20) G2: MSM(s, k_i G) == (sum s_i k_i) G.  G2 at this size takes the batched affine accumulation."""
+    from util import R, ints_to_array, rand_scalars
+    for g2, lg in ((False, 22), (True, 20)):
+        n = 1 << lg
+        k, kv = rand_scalars(rng, n)
+        s, sv = rand_scalars(rng, n)
+        pts = synth.fixed_base(gpu, k, g2=g2)
+        cfg = pkg.MSMConfig.default()
+        cfg.are_points_montgomery_form = True
+        cfg.precompute_factor = 16
+        table = gpu.msm_precompute_bases(pts, cfg, g2=g2)
+        info = (C.c_int32 * 8)()
+        assert gpu.dll.b200_msm_plan_info(C.c_int(n), C.c_int(0), C.c_int(254), C.c_int(16), C.c_int(int(g2)), info, None) == 0
+        assert info[3] == 1 and info[1] <= 16  # one bucket set: every window served by a precomputed multiple
+        got = gpu.msm(s, table, cfg, g2=g2, msm_size=n)[0]
+        dot = sum(a * b for a, b in zip(sv, kv)) % R
+        want = gpu.mul_scalar(gpu.generator(g2=g2), ints_to_array([dot])[0], g2=g2)
+        assert np.array_equal(gpu.to_affine(got, g2=g2), gpu.to_affine(want, g2=g2)), g2
+
+
+@pytest.mark.parametrize("precompute", [1, 16])
+def test_config0_100k_proof_byte_identical_to_reference_pipeline(gpu, ref, precompute):
+    """BASELINE configs[0] (benchmark/100k): the GPU proof.json equals the reference CPU pipeline's byte for byte, for
+    fixed non-trivial (r, s), without and with the precompute tables."""
+    zkey, wtns, vk = synth.make_complex_circuit(gpu, 100_000)
+    proof_ref, public = G.prove(ref, pkg.bindings, zkey, wtns, FIXED_R, FIXED_S)
+    assert G.verify(ref, proof_ref, public, vk)
+    cache = pkg.ZKeyCache(gpu, zkey, precompute=precompute)
+    try:
+        p, _ = cache.prove(wtns_words(wtns), FIXED_R, FIXED_S)
+        assert pkg.proof_json(p) == G.proof_json(proof_ref)
+    finally:
+        cache.close()
+
+
 def test_aadhaar_shaped_substitute_matches_oracle(gpu, ref):
     """configs[3] substitute (anon_aadhaar itself needs circom/circomlib/snarkjs): random satisfiable R1CS with
     multi-entry rows (collisions in the A/B accumulation), 9 public inputs and a ~90 % 0/1 witness (giant buckets:

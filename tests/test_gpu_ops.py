@@ -124,7 +124,7 @@ def test_msm_g1_matches_reference(gpu, ref, rng, n):
     assert ref.eq(got[0], want[0]) and affine_eq(ref, got[0], want[0])
 
 
-@pytest.mark.parametrize("n", [1, 5, 64, 1000, 1 << 14])
+@pytest.mark.parametrize("n", [1, 5, 64, 1000, 1 << 14, 1 << 18])
 def test_msm_g2_matches_reference(gpu, ref, rng, n):
     sc, pts = _msm_inputs(ref, rng, n, g2=True)
     got = gpu.msm(sc, pts, g2=True)
@@ -202,6 +202,61 @@ def test_msm_skewed_distribution(gpu, ref, rng, n):
     got = gpu.msm(sc, pts)
     want = ref.msm(sc, pts)
     assert affine_eq(ref, got[0], want[0])
+
+
+@pytest.mark.parametrize("bitsize", [1, 64, 128])
+def test_msm_bitsize(gpu, ref, rng, bitsize):
+    # MSMConfig.bitsize: scalars known to be shorter than 254 bits (msm.h:44-47); fewer windows, same sum
+    n = 2000
+    sc, pts = _msm_inputs(ref, rng, n)
+    mask = np.zeros(8, dtype=np.uint32)
+    for b in range(bitsize):
+        mask[b // 32] |= np.uint32(1 << (b % 32))
+    sc &= mask
+    cfg = B.MSMConfig.default()
+    cfg.bitsize = bitsize
+    got = gpu.msm(sc, pts, cfg)
+    want = ref.msm(sc, pts)
+    assert affine_eq(ref, got[0], want[0])
+
+
+@pytest.mark.parametrize("shared", [True, False])
+def test_msm_precompute_batch(gpu, ref, rng, shared):
+    # precompute_factor x batch, shared and per-MSM point sets (msm/tests.rs:167-252)
+    n, batch, f = 150, 3, 4
+    cfg = B.MSMConfig.default()
+    cfg.batch_size, cfg.are_points_shared_in_batch, cfg.precompute_factor = batch, shared, f
+    sc, _ = rand_scalars(rng, n * batch)
+    pts = ref.generate_affine_points(n if shared else n * batch)
+    plain = B.MSMConfig.default()
+    plain.batch_size, plain.are_points_shared_in_batch = batch, shared
+    want = ref.msm(sc, pts, plain)
+    table = gpu.msm_precompute_bases(pts, cfg)
+    got = gpu.msm(sc, table, cfg, msm_size=n)
+    for b in range(batch):
+        assert affine_eq(ref, got[b], want[b]), b
+
+
+def test_division_step_inverse_on_device(gpu):
+    # csrc/field_inv.cuh on the GPU: 2^17 inversions per field against x * x^-1 == 1 (and Fermat on the first few)
+    f = pkg.tools_lib().b200_inv_check
+    f.argtypes = [C.c_int, C.c_uint64, C.c_int, C.c_int]
+    assert f(1 << 17, 11, 1, 1) == 0 and f(1 << 17, 12, 0, 1) == 0
+
+
+def test_msm_suite_with_batched_affine_forced():
+    """The whole MSM parity suite again with the batched affine accumulation forced on for G1 and G2 at every size
+    (B200_BATCH_AFFINE is read once per process, hence the subprocess): tiny buckets, empty buckets, identities, repeated
+    and opposite points, the skewed distributions' giant buckets (the long-leftover CTA path)."""
+    import os
+    import subprocess
+    import sys
+    if os.environ.get("B200_BATCH_AFFINE") == "3":
+        pytest.skip("already inside the forced run")
+    env = dict(os.environ, B200_BATCH_AFFINE="3")
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-m", "gpu", "-x", "-q", "-k", "msm and not forced"],
+                       env=env, capture_output=True, text=True, timeout=1200, cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
 
 
 def test_msm_all_zero_and_empty(gpu, ref, rng):
@@ -331,11 +386,12 @@ def test_ntt_errors_are_codes_not_exceptions(gpu, rng, domains):
         gpu.ntt(big, B.kForward)  # larger than the domain (the reference throws across the ABI here)
 
 
-def test_ntt_full_size_properties(gpu, rng):
-    """BASELINE size (2^22, batch 3, in place on the device): iNTT(NTT(x)) == x and linearity NTT(x + y) == NTT(x) + NTT(y)
-    - size-independent properties where the CPU reference would take tens of seconds."""
+@pytest.mark.parametrize("logn,batch", [(22, 3), (24, 1)])
+def test_ntt_full_size_properties(gpu, rng, logn, batch):
+    """BASELINE sizes (2^22 batch 3 as in the prover; 2^24, the top of the configs[4] sweep), in place on the device:
+    iNTT(NTT(x)) == x, linearity NTT(x + y) == NTT(x) + NTT(y), and the known answer NTT(e_1)[k] == w^k -
+    size-independent properties where the CPU reference would take tens of seconds."""
     import torch
-    logn, batch = 22, 3
     n = 1 << logn
     gpu.ntt_release_domain()
     gpu.ntt_init_domain(gpu.get_root_of_unity(n))
@@ -368,5 +424,14 @@ def test_ntt_full_size_properties(gpu, rng):
         back = ntt(fx.clone(), B.kInverse, inplace=True)
         assert torch.equal(back, x)
         assert not torch.equal(fx, x)
+        # known answer: the transform of the unit vector e_1 is the sequence of powers of the domain generator
+        e1 = torch.zeros_like(x)
+        for b in range(batch):
+            e1[b * n + 1, 0] = 1
+        fe = ntt(e1, B.kForward).cpu().numpy().view(np.uint32)
+        w = from_words(gpu.get_root_of_unity(n))
+        for k in [0, 1, 2, 12345, n // 2, n - 1]:
+            for b in range(batch):
+                assert from_words(fe[b * n + k]) == pow(w, k, R), (k, b)
     finally:
         gpu.ntt_release_domain()

@@ -89,22 +89,12 @@ def test_python_oracle_agrees_with_host_helpers(lib, rng):
         assert got2 == O.G2.mul(O.G2.gen, sv[i])
 
 
-@pytest.mark.parametrize("g2", [0, 1])
-def test_batched_affine_bucket_model_matches_xyzz_accumulation(lib, g2):
-    """csrc/batch_affine.cuh + research/batch_affine_model.cu (DESIGN.md section 8.1, next kernel generation): pairwise-tree rounds
-    with a two-level Montgomery trick - executed with the very per-thread bodies the experimental kernels wrap -
-    reproduce the bucket sums of today's XYZZ accumulation on data with repeated points (tangent case), opposite points
-    (cancellation), identities, empty buckets and one giant bucket; with long buckets they spend 7.7-8.9 field products
-    per addition on this adversarial data (true inversions included) where the XYZZ mixed add spends 10."""
+@pytest.mark.parametrize("fq", [0, 1])
+def test_division_step_inverse_matches_fermat_on_host(lib, fq):
+    """csrc/field_inv.cuh (the shared inversion of the batched affine accumulation): x * inverse_safegcd(x) == 1 for
+    random Montgomery residues and the edge values 0 -> 0, 1, -1, raw 1, a power of two; equal to Fermat's inverse."""
     import ctypes as C
     import icicle_snark_b200 as pkg
-    f = pkg.tools_lib().b200_batch_affine_selfcheck
-    for n, nb, rounds in ((0, 4, -1), (1, 1, -1), (2, 1, -1), (5000, 37, -1), (20000, 512, -1), (3000, 3, -1),
-                          (4000, 64, 2), (9000, 1000, -1), (6000, 10, 0), (6000, 10, 1), (70000, 300, 5)):
-        ppa = C.c_double(0)
-        assert f(g2, n, nb, rounds, 99 + n, C.byref(ppa)) == 0, (n, nb, rounds)
-        if n >= 100 * nb and rounds < 0:
-            # long buckets (the prover's are ~80 entries). The count includes the true inversions (384 products per
-            # 512 slots) and this data's ~13 % trivial pairs (identities, cancellations), which cost slots but add nothing
-            assert 6.0 < ppa.value < 9.5, ppa.value
-    assert f(g2, -1, 4, -1, 0, None) == -1 and f(g2, 10, 0, -1, 0, None) == -1
+    f = pkg.tools_lib().b200_inv_check
+    f.argtypes = [C.c_int, C.c_uint64, C.c_int, C.c_int]
+    assert f(3000, 20261017 + fq, fq, 0) == 0
