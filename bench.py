@@ -3,6 +3,7 @@
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--constraints C] [--precompute F]
   python bench.py --impl reference ...        # the reference's own CPU implementation of the path, same instance
+  python bench.py --impl reference-cuda ...   # the reference's own CUDA backend rebuilt for sm_100a (oracle/_ref_cuda), same GPU
   python bench.py --sweep                     # standalone BN254 MSM / NTT sweeps (BASELINE configs[4]) folded into `extras`
 
 A "step" is one proof of the synthetic ComplexCircuit(C, C) instance (the reference's benchmark circuit,
@@ -36,7 +37,7 @@ sys.path.insert(0, ROOT)
 
 R_MOD = 0x30644E72E131A029B85045B68181585D2833E84879B9709143E1F593F0000001
 CPU_SAMPLE_CONSTRAINTS = 400_000  # bounded CPU sample of the product arm's cpu_baseline (~5 s per proof on 16 cores)
-REF_WALL_BUDGET_S = float(os.environ.get("B200_REF_BUDGET_S", "1300"))  # reference arm: proofs at the real size until this
+REF_WALL_BUDGET_S = float(os.environ.get("B200_REF_BUDGET_S", "900"))  # reference arm: proofs at the real size until this
 INSTANCE_DIR = os.environ.get("B200_BENCH_CACHE", os.path.join(ROOT, ".bench_cache"))
 # fixed, non-trivial blinding factors (the epilogue's host scalar multiplications are inside the timed region)
 R_BLIND = int.from_bytes(hashlib.sha256(b"icicle-snark-b200 bench r").digest(), "big") % R_MOD
@@ -213,6 +214,55 @@ def run_reference(args):
     return 0
 
 
+def run_reference_cuda(args):
+    """Second baseline (SURVEY 8c / BASELINE.md 3): the reference's CUDA backend, recompiled for sm_100a from its own
+    sources (oracle/Makefile.ref_cuda), driven through the reference frontend by the restated Rust host with the Rust
+    code's residency (oracle/groth16_ref_cuda.py).  Wall clock per proof, warm cache, witness from host memory."""
+    if int(os.environ.get("RANK", 0)) != 0:
+        return 0
+    import __graft_entry__ as ge
+    pkg = ge.load_package()
+    from oracle import groth16_ref as G
+    from oracle import groth16_ref_cuda as GC
+    n = args.constraints
+    if not GC.available():
+        print(json.dumps({"impl": "reference-cuda", "unavailable": "oracle/_ref_cuda is not built (needs /root/reference at build time)"}), flush=True)
+        return 0
+    zkey, wtns, vk = reference_instance(n)
+    ref = GC.ref_cuda(0)
+    t0 = time.time()
+    cache = GC.ZKeyCacheCuda(ref, pkg.bindings, zkey)
+    ref.device_synchronize()
+    t_cache = time.time() - t0
+    del zkey
+    times, parts, proof, public = [], [], None, None
+    warm = max(1, min(args.warmup, 2))
+    for i in range(warm + args.steps):
+        tm = {}
+        proof, public = GC.prove(ref, pkg.bindings, wtns, R_BLIND, S_BLIND, cache, timings=tm)
+        if i >= warm:
+            times.append(tm["total_s"] * 1e3)
+            parts.append((tm["r1cs_ntt_s"] * 1e3, tm["msm_s"] * 1e3))
+        log(f"reference-cuda arm: proof {i} took {tm['total_s'] * 1e3:.0f} ms (r1cs+ntt {tm['r1cs_ntt_s'] * 1e3:.0f}, msm {tm['msm_s'] * 1e3:.0f})")
+    ref.set_device("CPU", 0)
+    ok = bool(G.verify(ref, proof, public, vk))
+    ms = sum(times) / len(times)
+    out = {
+        "impl": "reference-cuda", "metric": f"groth16_prove_latency_ms_{n // 1000}k", "value": ms, "unit": "ms", "n_gpus": 1,
+        "steps": len(times), "warmup": warm, "ms_per_step": ms, "higher_is_better": False, "scaling": "strong", "vs_baseline": None,
+        "dtype": "u32x8 (254-bit modular integers)", "data": "synthetic",
+        "config": {"workload": f"ComplexCircuit({n},{n}) Groth16 prove, warm cache", "timing": "wall clock around the restated Rust host; copies included as in the Rust code",
+                   "backend": "ICICLE 3.8.0 CUDA backend, nvcc -O3 sm_100a, unmodified sources", "blinding": "fixed non-trivial r, s (same as the product arm)",
+                   "host_glue": "the Rust host's gather / scatter / copies restated in numpy (single thread): the r1cs+ntt share is an upper bound for the Rust+rayon host, the msm share is the reference's own GPU code alone"},
+        "phases_ms": {"r1cs_ntt_ms": round(sum(x[0] for x in parts) / len(parts), 1), "msm_ms": round(sum(x[1] for x in parts) / len(parts), 1)},
+        "e2e": {"value": ms, "unit": "ms", "h2d_bytes_per_step": None, "d2h_bytes_per_step": None},
+        "verified": ok, "cache_build_s": round(t_cache, 2), "proof_json_sha256": hashlib.sha256(G.proof_json(proof).encode()).hexdigest(),
+        "min_ms": min(times), "max_ms": max(times),
+    }
+    print(json.dumps(out), flush=True)
+    return 0
+
+
 # ------------------------------------------------------------------------------------------------ product arm
 def plan_info(lib, n, factor, g2=False, c=0):
     out = (C.c_int32 * 8)()
@@ -239,7 +289,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference", "reference-cuda"])
     ap.add_argument("--constraints", type=int, default=3_200_000)
     ap.add_argument("--precompute", type=int, default=int(os.environ.get("B200_PRECOMPUTE", "16")))
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -252,6 +302,8 @@ def main():
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
+    if args.impl == "reference-cuda":
+        return run_reference_cuda(args)
     args.warmup = max(args.warmup, 3)
 
     import torch
@@ -499,7 +551,7 @@ def main():
                    "timing": "host clock around the synchronous C-ABI call + cuda sync + barrier, max over ranks"},
         "e2e": {"value": ms_e2e, "unit": "ms", "h2d_bytes_per_step": nw * 32, "d2h_bytes_per_step": 576 if world == 1 else 576 * world,
                 "note": "h2d bytes are per rank that evaluates R1CS rows (all ranks when the quotient chain is replicated; the 3 polynomial owners when it is split, the others upload only their 1/N witness slice)"},
-        "verified": verified, "gpu_launches": int(launches), "clocks": clocks, "phases_ms": phases, "roofline": roofline,
+        "verified": verified, "proof_json_sha256": hashlib.sha256(pkg.proof_json(proof).encode()).hexdigest(), "gpu_launches": int(launches), "clocks": clocks, "phases_ms": phases, "roofline": roofline,
         "cpu_baseline": cpu_baseline, "extras": extras,
     }
     print(json.dumps(out), flush=True)

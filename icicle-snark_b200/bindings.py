@@ -257,9 +257,10 @@ class IcicleLib:
         return out
 
     def msm_precompute_bases(self, points, cfg, g2=False, n=None, out=None):
-        n = points.shape[0] if n is None else n
+        sets = 1 if (cfg.are_points_shared_in_batch or cfg.batch_size < 1) else cfg.batch_size
+        n = points.shape[0] // sets if n is None else n  # per-MSM size; the table covers n * sets points (msm/mod.rs:156-197)
         aw = G2_AFFINE_WORDS if g2 else G1_AFFINE_WORDS
-        out = words(n * cfg.precompute_factor, aw) if out is None else out
+        out = words(n * sets * cfg.precompute_factor, aw) if out is None else out
         fn = self.dll.bn254_g2_msm_precompute_bases if g2 else self.dll.bn254_msm_precompute_bases
         check(fn(_ptr(points), C.c_int(n), C.byref(cfg), _ptr(out)), "bn254_msm_precompute_bases")
         return out

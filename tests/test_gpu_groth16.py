@@ -189,6 +189,35 @@ def test_config0_100k_proof_byte_identical_to_reference_pipeline(gpu, ref, preco
         cache.close()
 
 
+@pytest.mark.parametrize("n", [30_000, 800_000])
+def test_reference_cuda_backend_agrees_byte_for_byte(gpu, ref, n):
+    """Second oracle: the reference's own CUDA backend, rebuilt for sm_100a from its sources
+    (oracle/Makefile.ref_cuda) and driven by the restated Rust host with the Rust code's residency
+    (oracle/groth16_ref_cuda.py), proves the same instance with the same (r, s) on this GPU: proof.json must be
+    identical to the product's - at 800k, a BASELINE size where the CPU oracle is too slow to run in a test."""
+    from oracle import groth16_ref_cuda as GC
+    if not GC.available():
+        pytest.skip("oracle/_ref_cuda not built (needs /root/reference at build time)")
+    zkey, wtns, vk = synth.make_complex_circuit(gpu, n, seed=b"refcuda%d" % n)
+    rc = GC.ref_cuda(0)
+    try:
+        cache_ref = GC.ZKeyCacheCuda(rc, pkg.bindings, zkey)
+        try:
+            proof_ref, public = GC.prove(rc, pkg.bindings, wtns, FIXED_R, FIXED_S, cache_ref)
+        finally:
+            cache_ref.close()
+            rc.ntt_release_domain()
+    finally:
+        rc.set_device("CPU", 0)
+    assert G.verify(ref, proof_ref, public, vk)
+    cache = pkg.ZKeyCache(gpu, zkey, precompute=16)
+    try:
+        p, _ = cache.prove(wtns_words(wtns), FIXED_R, FIXED_S)
+        assert pkg.proof_json(p) == G.proof_json(proof_ref)
+    finally:
+        cache.close()
+
+
 def test_aadhaar_shaped_substitute_matches_oracle(gpu, ref):
     """configs[3] substitute (anon_aadhaar itself needs circom/circomlib/snarkjs): random satisfiable R1CS with
     multi-entry rows (collisions in the A/B accumulation), 9 public inputs and a ~90 % 0/1 witness (giant buckets:
