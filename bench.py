@@ -48,6 +48,25 @@ def log(*a):
     print("[bench]", *a, file=sys.stderr, flush=True)
 
 
+# stdout carries exactly ONE JSON line: native libraries (NCCL's version banner, ...) write to fd 1 directly, so fd 1 is
+# pointed at stderr for the whole run and the result line goes to the saved descriptor
+_RESULT_FD = None
+
+
+def guard_stdout():
+    global _RESULT_FD
+    if _RESULT_FD is None:
+        sys.stdout.flush()
+        _RESULT_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(obj):
+    line = (json.dumps(obj) + "\n").encode()
+    sys.stdout.flush()
+    os.write(_RESULT_FD if _RESULT_FD is not None else 1, line)
+
+
 # ------------------------------------------------------------------------------------------------ clocks
 class ClockSampler:
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
@@ -210,7 +229,7 @@ def run_reference(args):
         "e2e": {"value": ms, "unit": "ms", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "verified": ok, "gpu_launches": 0,
     }
-    print(json.dumps(out), flush=True)
+    emit(out)
     return 0
 
 
@@ -226,7 +245,7 @@ def run_reference_cuda(args):
     from oracle import groth16_ref_cuda as GC
     n = args.constraints
     if not GC.available():
-        print(json.dumps({"impl": "reference-cuda", "unavailable": "oracle/_ref_cuda is not built (needs /root/reference at build time)"}), flush=True)
+        emit({"impl": "reference-cuda", "unavailable": "oracle/_ref_cuda is not built (needs /root/reference at build time)"})
         return 0
     zkey, wtns, vk = reference_instance(n)
     ref = GC.ref_cuda(0)
@@ -259,7 +278,7 @@ def run_reference_cuda(args):
         "verified": ok, "cache_build_s": round(t_cache, 2), "proof_json_sha256": hashlib.sha256(G.proof_json(proof).encode()).hexdigest(),
         "min_ms": min(times), "max_ms": max(times),
     }
-    print(json.dumps(out), flush=True)
+    emit(out)
     return 0
 
 
@@ -296,10 +315,14 @@ def main():
     ap.add_argument("--no-verify", action="store_true", help="skip the pairing checks of the last timed proof (debug only)")
     ap.add_argument("--sweep", action="store_true", help="add the standalone MSM / NTT sweeps (configs[4]) to `extras`")
     ap.add_argument("--split-quotient", type=int, default=1, help="N>1: split the three quotient polynomials across ranks (0 = replicate)")
+    ap.add_argument("--exchange", default="lib", choices=["lib", "torch"],
+                    help="N>1: who moves the data: 'lib' = b200_groth16_prove_sharded (NCCL inside the C library, no host in the "
+                         "exchange), 'torch' = commit_begin / torch.distributed scatter + all_gather / commit_end")
     ap.add_argument("--shard-skew", type=float, default=0.049,
                     help="N>1 with the quotient split: the polynomial owners get smaller witness-MSM shards "
                          "(b200_shard_range; = one polynomial's transform time / all witness MSMs' time; 0 = equal shards)")
     args = ap.parse_args()
+    guard_stdout()
     if args.impl == "reference":
         return run_reference(args)
     if args.impl == "reference-cuda":
@@ -348,13 +371,17 @@ def main():
     w_dev = w_pinned.cuda()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
 
-    qx = pkg.multi_gpu.QuotientExchange(cache, torch.device("cuda", local)) if (world > 1 and args.split_quotient) else None
+    use_lib = world > 1 and args.split_quotient and args.exchange == "lib"
+    comm = pkg.multi_gpu.LibComm.from_torch(lib) if use_lib else None
+    qx = pkg.multi_gpu.QuotientExchange(cache, torch.device("cuda", local)) if (world > 1 and args.split_quotient and not use_lib) else None
 
     def step(witness_ptr):
         """one proof; returns the proof struct on rank 0"""
         if world == 1:
             proof, tm = cache.prove(witness_ptr, R_BLIND, S_BLIND, n_witness=nw)
             return proof, tm
+        if comm is not None:  # everything inside the library: grouped send/recv of the slices + one 576 B all-gather
+            return cache.prove_sharded(comm, witness_ptr, R_BLIND, S_BLIND, n_witness=nw)
         if qx is not None:  # quotient chain split across ranks: one scatter per polynomial over NVLink
             parts, tm = qx.commit(witness_ptr, n_witness=nw)
         else:               # quotient chain replicated on every rank
@@ -399,7 +426,7 @@ def main():
         return float(t.item())
 
     ms_dev, ms_e2e = agg(per_dev), agg(per_e2e)
-    if world > 1 and qx is not None:
+    if world > 1 and (qx is not None or comm is not None):
         # cross-check of the split path: the replicated-chain proof (same r, s) must be identical
         parts_r, _ = cache.commit_partials(w_dev.data_ptr(), n_witness=nw)
         plist_r = pkg.multi_gpu.all_gather_partials(parts_r, torch.device("cuda", local))
@@ -546,7 +573,7 @@ def main():
         "warmup": args.warmup, "ms_per_step": ms_dev, "higher_is_better": False, "scaling": "strong", "vs_baseline": None,
         "dtype": "u32x8 (254-bit modular integers)", "data": "synthetic",
         "config": {"workload": f"ComplexCircuit({n},{n}) Groth16 prove, warm ZKeyCache", "n_vars": cache.n_vars,
-                   "domain_size": cache.domain_size, "precompute_factor": args.precompute, "parallelism": f"msm-shard{world}" + ("+quotient-split" if qx is not None else "") + (f"+shard-skew{skew:g}" if skew > 0 else ""),
+                   "domain_size": cache.domain_size, "precompute_factor": args.precompute, "parallelism": f"msm-shard{world}" + ("+quotient-split" if (qx is not None or comm is not None) else "") + ("+in-library-nccl" if comm is not None else "") + (f"+shard-skew{skew:g}" if skew > 0 else ""),
                    "blinding": "fixed non-trivial r, s", "l2": "256 MiB flush between timed iterations",
                    "timing": "host clock around the synchronous C-ABI call + cuda sync + barrier, max over ranks"},
         "e2e": {"value": ms_e2e, "unit": "ms", "h2d_bytes_per_step": nw * 32, "d2h_bytes_per_step": 576 if world == 1 else 576 * world,
@@ -554,7 +581,7 @@ def main():
         "verified": verified, "proof_json_sha256": hashlib.sha256(pkg.proof_json(proof).encode()).hexdigest(), "gpu_launches": int(launches), "clocks": clocks, "phases_ms": phases, "roofline": roofline,
         "cpu_baseline": cpu_baseline, "extras": extras,
     }
-    print(json.dumps(out), flush=True)
+    emit(out)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

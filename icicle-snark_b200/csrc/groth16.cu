@@ -36,6 +36,7 @@
 #include <vector>
 
 #include "host_math.h"
+#include "comm.cuh"
 #include "msm.cuh"
 #include "ntt.cuh"
 #include "staging.cuh"
@@ -177,6 +178,11 @@ struct b200_zkey_cache {
               ev_g2 = nullptr, ev_q = nullptr, ev_prev = nullptr, ev_b1 = nullptr;
   std::mutex mu;
   bool in_flight = false; // commit_begin succeeded and holds `mu` until commit_end
+  // in-library exchange of the sharded prover (b200_groth16_prove_sharded): this rank's slice of the three transformed
+  // polynomials, every rank's partial sums
+  Fr* qx_slices = nullptr;
+  uint8_t *d_all_parts = nullptr, *h_all_parts = nullptr;
+  cudaEvent_t ev_slice = nullptr;
 };
 
 namespace b200 {
@@ -236,10 +242,12 @@ namespace b200 {
     if (!c) return;
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
-    void* ptrs[] = {c->idxB, c->d_wb, c->pA, c->pB1, c->pC, c->pH, c->pB2, c->row_ptr, c->col, c->val, c->keys, c->d_witness, c->d_vec, c->d_h, c->d_results, c->d_scratch_results};
+    void* ptrs[] = {c->idxB, c->d_wb, c->pA, c->pB1, c->pC, c->pH, c->pB2, c->row_ptr, c->col, c->val, c->keys, c->d_witness, c->d_vec, c->d_h, c->d_results, c->d_scratch_results, c->qx_slices, c->d_all_parts};
     for (void* p : ptrs)
       if (p) cudaFree(p);
     if (c->h_results) cudaFreeHost(c->h_results);
+    if (c->h_all_parts) cudaFreeHost(c->h_all_parts);
+    if (c->ev_slice) cudaEventDestroy(c->ev_slice);
     cudaStream_t ss[] = {c->s_copy, c->s_g1, c->s_g2, c->s_q};
     for (auto s : ss)
       if (s) cudaStreamDestroy(s);
@@ -578,6 +586,25 @@ namespace b200 {
       if (!d || d->max_log < (int)c->power) B200_TRY(ntt_init_domain_host(host_omega((int)c->power), c->s_copy));
     }
     B200_CUDA(cudaEventRecord(c->ev_start, c->s_copy), ICICLE_UNKNOWN_FALLBACK);
+    if (full && c->world > 1 && c->ev_slice && c->a_hi > c->a_lo) {
+      // sharded rank that also evaluates R1CS rows: its own slice first - the witness MSMs (s_g1, s_g2) start on it
+      // while the rest of the witness, which only the quotient chain reads, is still crossing PCIe
+      B200_CUDA(
+        cudaMemcpyAsync(c->d_witness + c->a_lo, witness + c->a_lo, (size_t)(c->a_hi - c->a_lo) * 32, cudaMemcpyDefault, c->s_copy),
+        ICICLE_COPY_FAILED);
+      B200_CUDA(cudaEventRecord(c->ev_slice, c->s_copy), ICICLE_UNKNOWN_FALLBACK);
+      for (cudaStream_t s : {c->s_g1, c->s_g2})
+        B200_CUDA(cudaStreamWaitEvent(s, c->ev_slice, 0), ICICLE_UNKNOWN_FALLBACK);
+      if (c->a_lo > 0)
+        B200_CUDA(cudaMemcpyAsync(c->d_witness, witness, (size_t)c->a_lo * 32, cudaMemcpyDefault, c->s_copy), ICICLE_COPY_FAILED);
+      if (c->a_hi < c->n_vars)
+        B200_CUDA(
+          cudaMemcpyAsync(c->d_witness + c->a_hi, witness + c->a_hi, (size_t)(c->n_vars - c->a_hi) * 32, cudaMemcpyDefault, c->s_copy),
+          ICICLE_COPY_FAILED);
+      B200_CUDA(cudaEventRecord(c->ev_h2d, c->s_copy), ICICLE_UNKNOWN_FALLBACK);
+      B200_CUDA(cudaStreamWaitEvent(c->s_q, c->ev_h2d, 0), ICICLE_UNKNOWN_FALLBACK);
+      return ICICLE_SUCCESS;
+    }
     const size_t w_lo = full ? 0 : c->a_lo, w_hi = full ? c->n_vars : c->a_hi;
     if (w_hi > w_lo)
       B200_CUDA(
@@ -1045,6 +1072,111 @@ eIcicleError b200_groth16_prove(
   B200_TRY(commit_wait(cache, &parts, tm));       // (always drain the enqueued proof before returning)
   B200_TRY(be);
   return finish_with(cache, &parts, 1, bt, proof);
+}
+
+// One proof over `comm->world` GPUs, one process per GPU, every rank calling with the same witness (HOST or DEVICE
+// memory) and its own shard of the cache (b200_zkey_cache_create_sharded with the communicator's rank / world).  The whole
+// data plane is inside the library: the quotient chain is split by polynomial (rank j transforms polynomial j),
+// the owners send every rank its H-shard slice with ONE grouped ncclSend/ncclRecv on the chain's stream, the H MSM follows
+// on the same stream, the witness MSMs run meanwhile on their own streams, one 576 B ncclAllGather collects the partial
+// sums and rank 0 folds + blinds.  The host waits once, at the end.  `proof` is written on rank 0 only (may be NULL elsewhere).
+eIcicleError b200_groth16_prove_sharded(
+  b200_zkey_cache* c, b200_comm* comm, const bn254_scalar_t* witness, uint32_t n_witness, const bn254_scalar_t* r,
+  const bn254_scalar_t* s, b200_groth16_proof* proof, b200_prove_timings* tm)
+{
+  if (!c || !comm || !witness) return ICICLE_INVALID_POINTER;
+  if (comm->rank != c->rank || comm->world != c->world || (comm->rank == 0 && !proof)) return ICICLE_INVALID_ARGUMENT;
+  if (!nccl().ok) return ICICLE_API_NOT_IMPLEMENTED;
+  const int world = c->world, rank = c->rank;
+  const uint32_t N = c->domain_size, cnt = c->h_hi - c->h_lo;
+  auto owner_of = [world](int j) { return world >= 3 ? j : (world == 2 ? (j < 2 ? 0 : 1) : 0); };
+  int first = 0, count = 0;
+  for (int j = 2; j >= 0; --j)
+    if (owner_of(j) == rank) {
+      first = j;
+      ++count;
+    }
+  std::lock_guard<std::mutex> g(c->mu);
+  B200_CUDA(cudaSetDevice(c->device), ICICLE_INVALID_DEVICE);
+  if (!c->d_all_parts) { // first sharded proof on this cache: exchange buffers
+    B200_CUDA(dev_alloc(&c->qx_slices, 3 * (size_t)(cnt ? cnt : 1), c), ICICLE_ALLOCATION_FAILED);
+    B200_CUDA(dev_alloc(&c->d_all_parts, (size_t)world * sizeof(b200_groth16_partials), c), ICICLE_ALLOCATION_FAILED);
+    B200_CUDA(cudaMallocHost((void**)&c->h_all_parts, (size_t)world * sizeof(b200_groth16_partials)), ICICLE_ALLOCATION_FAILED);
+    B200_CUDA(cudaEventCreateWithFlags(&c->ev_slice, cudaEventDisableTiming), ICICLE_UNKNOWN_FALLBACK);
+    // result slots no MSM of this rank ever writes (empty shards) hold the identity
+    static const G1Projective id1 = {Fq::zero(), Fq::raw_one(), Fq::zero()};
+    static const G2Projective id2 = {Fq2::zero(), {Fq::raw_one(), Fq::zero()}, Fq2::zero()};
+    ResultSlots rs = result_slots(c);
+    for (G1Projective* p : {rs.a, rs.b1, rs.c, rs.h})
+      B200_CUDA(cudaMemcpy(p, &id1, 96, cudaMemcpyHostToDevice), ICICLE_COPY_FAILED);
+    B200_CUDA(cudaMemcpy(rs.b2, &id2, 192, cudaMemcpyHostToDevice), ICICLE_COPY_FAILED);
+  }
+  eIcicleError e = enqueue_upload(c, witness, n_witness, count > 0);
+  if (e == ICICLE_SUCCESS && count > 0) e = enqueue_quotient_polys(c, first, count, c->d_vec + (size_t)first * N);
+  if (e == ICICLE_SUCCESS && count == 0) cudaEventRecord(c->ev_r1cs, c->s_q);
+  if (e == ICICLE_SUCCESS) e = enqueue_witness_msms(c);
+  if (e == ICICLE_SUCCESS) {
+    // the exchange: polynomial j's owner holds all of it; rank q needs [N q / world, N (q+1) / world)
+    ncclResult_t nr = nccl().GroupStart();
+    for (int j = 0; j < 3 && nr == ncclSuccess; ++j) {
+      const int owner = owner_of(j);
+      Fr* mine = c->qx_slices + (size_t)j * cnt;
+      if (owner == rank) {
+        const Fr* poly = c->d_vec + (size_t)j * N;
+        for (int q = 0; q < world && nr == ncclSuccess; ++q) {
+          uint32_t lo, hi;
+          shard(N, q, world, &lo, &hi);
+          if (hi == lo) continue;
+          if (q == rank)
+            cudaMemcpyAsync(mine, poly + lo, (size_t)(hi - lo) * 32, cudaMemcpyDeviceToDevice, c->s_q);
+          else
+            nr = nccl().Send(poly + lo, (size_t)(hi - lo) * 32, ncclUint8, q, comm->comm, c->s_q);
+        }
+      } else if (cnt) {
+        nr = nccl().Recv(mine, (size_t)cnt * 32, ncclUint8, owner, comm->comm, c->s_q);
+      }
+    }
+    ncclResult_t ge = nccl().GroupEnd();
+    if (nr != ncclSuccess || ge != ncclSuccess) {
+      fprintf(stderr, "[icicle_b200] quotient exchange: %s\n", nccl().GetErrorString(nr != ncclSuccess ? nr : ge));
+      e = (eIcicleError)ICICLE_UNKNOWN_FALLBACK;
+    }
+  }
+  // d_vec order: 0 = B.w', 1 = A.w', 2 = product'; enqueue_h takes (a, b, c) = (A', B', product')
+  if (e == ICICLE_SUCCESS) e = enqueue_h(c, c->qx_slices + (size_t)cnt, c->qx_slices, c->qx_slices + 2 * (size_t)cnt);
+  BlindTerms bt;
+  eIcicleError be = ICICLE_SUCCESS;
+  if (e == ICICLE_SUCCESS) {
+    for (cudaEvent_t ev : {c->ev_q, c->ev_g1, c->ev_g2})
+      cudaStreamWaitEvent(c->s_copy, ev, 0);
+    ncclResult_t nr = nccl().AllGather(c->d_results, c->d_all_parts, sizeof(b200_groth16_partials), ncclUint8, comm->comm, c->s_copy);
+    if (nr != ncclSuccess) e = (eIcicleError)ICICLE_UNKNOWN_FALLBACK;
+    if (rank == 0)
+      cudaMemcpyAsync(c->h_all_parts, c->d_all_parts, (size_t)world * sizeof(b200_groth16_partials), cudaMemcpyDeviceToHost, c->s_copy);
+    cudaEventRecord(c->ev_prev, c->s_copy);
+    if (rank == 0) be = compute_blind(c, r, s, bt); // host work overlapped with the GPU
+  }
+  // the one host wait of the proof (also drains a failed enqueue so the next proof starts clean)
+  for (cudaStream_t st : {c->s_q, c->s_g1, c->s_g2, c->s_copy})
+    if (cudaStreamSynchronize(st) != cudaSuccess && e == ICICLE_SUCCESS) e = ICICLE_SYNCHRONIZATION_FAILED;
+  if (cudaGetLastError() != cudaSuccess && e == ICICLE_SUCCESS) e = (eIcicleError)ICICLE_UNKNOWN_FALLBACK;
+  if (e != ICICLE_SUCCESS) return e;
+  if (tm) {
+    float t_q = 0, t_g1 = 0, t_g2 = 0;
+    cudaEventElapsedTime(&tm->h2d_ms, c->ev_start, c->ev_h2d);
+    cudaEventElapsedTime(&tm->r1cs_ms, c->ev_h2d, c->ev_r1cs);
+    cudaEventElapsedTime(&tm->ntt_ms, c->ev_r1cs, c->ev_ntt);
+    cudaEventElapsedTime(&t_q, c->ev_start, c->ev_q);
+    cudaEventElapsedTime(&t_g1, c->ev_start, c->ev_g1);
+    cudaEventElapsedTime(&t_g2, c->ev_start, c->ev_g2);
+    tm->msm_g1_ms = t_g1;
+    tm->msm_g2_ms = t_g2;
+    tm->total_ms = std::max(t_q, std::max(t_g1, t_g2));
+    (void)cudaGetLastError();
+  }
+  if (rank != 0) return ICICLE_SUCCESS;
+  B200_TRY(be);
+  return finish_with(c, (const b200_groth16_partials*)c->h_all_parts, world, bt, proof);
 }
 
 // proof.json text for a proof struct (what b200_groth16_prove_files writes); returns the length, or 0 if cap is too small

@@ -79,3 +79,54 @@ class QuotientExchange:
         self.torch.cuda.current_stream().synchronize()
         # d_vec order: 0 = B.w', 1 = A.w', 2 = product'; commit_end takes (a, b, c) = (A', B', product')
         return self.cache.commit_end(self.slices[1].data_ptr(), self.slices[0].data_ptr(), self.slices[2].data_ptr())
+
+
+# ---- the library's own communicator (include/icicle_b200.h: b200_comm_*) ------------------------------------------
+class LibComm:
+    """NCCL communicator owned by the C library: rank 0 draws the rendezvous token, `bcast` (any callable that returns
+    rank 0's 128 bytes on every rank - torch.distributed here, an MPI / TCP broadcast in another host) distributes it."""
+
+    def __init__(self, lib, rank, world, bcast):
+        self.lib, self.rank, self.world = lib, rank, world
+        token = (C.c_uint8 * 128)()
+        if rank == 0:
+            rc = lib.dll.b200_comm_unique_id(token)
+            if rc != 0:
+                raise RuntimeError(f"b200_comm_unique_id failed: {rc} (no libnccl.so.2?)")
+        raw = bcast(bytes(token))
+        token = (C.c_uint8 * 128).from_buffer_copy(raw)
+        h = C.c_void_p()
+        rc = lib.dll.b200_comm_create(token, C.c_int(rank), C.c_int(world), C.byref(h))
+        if rc != 0:
+            raise RuntimeError(f"b200_comm_create failed: {rc}")
+        self.handle = h
+
+    @classmethod
+    def from_torch(cls, lib):
+        import torch
+        import torch.distributed as dist
+        rank, world = dist.get_rank(), dist.get_world_size()
+
+        def bcast(raw):
+            t = torch.frombuffer(bytearray(raw), dtype=torch.uint8)
+            if dist.get_backend() == "nccl":
+                t = t.cuda()
+            dist.broadcast(t, src=0)
+            return bytes(t.cpu().numpy().tobytes())
+
+        return cls(lib, rank, world, bcast)
+
+    def msm(self, scalars, points, local_size, cfg, g2=False):
+        """Sharded standalone MSM (b200_msm_sharded): this rank's slice in, the total (host, projective) out."""
+        out = np.zeros(48 if g2 else 24, dtype=np.uint32)
+        sp = C.c_void_p(scalars) if isinstance(scalars, int) else scalars.ctypes.data_as(C.c_void_p)
+        pp = C.c_void_p(points) if isinstance(points, int) else points.ctypes.data_as(C.c_void_p)
+        rc = self.lib.dll.b200_msm_sharded(self.handle, sp, pp, C.c_int(local_size), C.byref(cfg), C.c_int(int(g2)), out.ctypes.data_as(C.c_void_p))
+        if rc != 0:
+            raise RuntimeError(f"b200_msm_sharded failed: {rc}")
+        return out
+
+    def close(self):
+        if self.handle:
+            self.lib.dll.b200_comm_destroy(self.handle)
+            self.handle = None

@@ -60,6 +60,17 @@ class ZKeyCache:
               "b200_groth16_prove")
         return proof, tm
 
+    def prove_sharded(self, comm, witness, r=None, s=None, n_witness=None):
+        """One proof over the communicator's GPUs with the whole exchange inside the library
+        (b200_groth16_prove_sharded); returns (proof on rank 0 / None elsewhere, timings)."""
+        proof, tm = Groth16Proof(), ProveTimings()
+        wp, n = self._wptr(witness, n_witness)
+        rp = None if r is None else np.frombuffer(int(r).to_bytes(32, "little"), dtype=np.uint32).ctypes.data_as(C.c_void_p)
+        sp = None if s is None else np.frombuffer(int(s).to_bytes(32, "little"), dtype=np.uint32).ctypes.data_as(C.c_void_p)
+        check(self.lib.dll.b200_groth16_prove_sharded(self.handle, comm.handle, wp, C.c_uint32(n), rp, sp, C.byref(proof), C.byref(tm)),
+              "b200_groth16_prove_sharded")
+        return (proof if comm.rank == 0 else None), tm
+
     def commit_partials(self, witness, n_witness=None):
         parts, tm = Groth16Partials(), ProveTimings()
         wp, n = self._wptr(witness, n_witness)

@@ -315,6 +315,29 @@ eIcicleError b200_zkey_cache_b_points(const b200_zkey_cache* cache, uint32_t* ke
 eIcicleError b200_groth16_finish(const b200_zkey_cache* cache, const b200_groth16_partials* parts, int n_parts,
                                  const bn254_scalar_t* r, const bn254_scalar_t* s, b200_groth16_proof* proof);
 
+/* ---- multi-GPU data plane inside the library (one process per GPU; NCCL resolved at run time, csrc/comm.cuh) --------
+ * The reference has no multi-GPU path (device 0 is hard-coded, src/lib.rs:29); these entry points are what a host in
+ * any language binds to shard one proof or one MSM over the GPUs of a box.
+ *   b200_comm_unique_id   rank 0 draws the 128-byte rendezvous token; the host hands it to the other ranks
+ *   b200_comm_create      collective: joins the communicator on the calling thread's active device
+ *   b200_groth16_prove_sharded  one proof over comm->world GPUs: every rank passes the same witness (host or device
+ *                         memory) and a cache built with b200_zkey_cache_create_sharded(rank, world); quotient-polynomial
+ *                         slices travel by one grouped ncclSend/ncclRecv on the library's streams, the partial sums by
+ *                         one 576-byte ncclAllGather; rank 0 folds, blinds and writes `proof` (others may pass NULL)
+ *   b200_msm_sharded      every rank holds a contiguous slice of scalars and points (same config semantics as
+ *                         bn254_msm / bn254_g2_msm); `result` (HOST memory, projective) holds the total on every rank
+ * ICICLE_API_NOT_IMPLEMENTED when no libnccl.so.2 can be loaded. */
+typedef struct b200_comm b200_comm;
+eIcicleError b200_comm_unique_id(uint8_t* id128);
+eIcicleError b200_comm_create(const uint8_t* id128, int rank, int world, b200_comm** out);
+eIcicleError b200_comm_destroy(b200_comm* comm);
+eIcicleError b200_comm_info(const b200_comm* comm, int* rank, int* world);
+eIcicleError b200_groth16_prove_sharded(b200_zkey_cache* cache, b200_comm* comm, const bn254_scalar_t* witness,
+                                        uint32_t n_witness, const bn254_scalar_t* r, const bn254_scalar_t* s,
+                                        b200_groth16_proof* proof, b200_prove_timings* timings);
+eIcicleError b200_msm_sharded(b200_comm* comm, const void* scalars, const void* points, int local_size,
+                              const MSMConfig* config, int g2, void* result);
+
 /* File-level mirror of `groth16_prove(witness, zkey, proof, public, device, &mut CacheManager)`
  * (src/lib.rs:33-61): reads .wtns/.zkey, keeps a process-wide cache keyed "{zkey}_{device}",
  * writes proof.json / public.json byte-for-byte as serde_json's pretty printer does. */

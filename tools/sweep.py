@@ -1,8 +1,9 @@
 #!/usr/bin/env python
 """Standalone sweeps (BASELINE.json configs[4]): BN254 G1/G2 MSM 2^16..2^26 points and Fr NTT 2^16..2^24,
 inputs resident in HBM, CUDA-event timing, one JSON line per point.  Under torchrun (N ranks) the MSM is
-sharded by contiguous point ranges (each rank runs the full Pippenger on n/N points; one 96 B/192 B all_gather
-+ N-1 host adds) and the NTT runs as N replicas (it does not shard).
+sharded by contiguous point ranges through the library's own entry point b200_msm_sharded (each rank runs the full
+Pippenger on n/N points; one 96 B/192 B ncclAllGather inside the library + N-1 host adds on every rank) and the NTT
+runs as N replicas (it does not shard).
 
   python tools/sweep.py [--msm 16,18,...] [--g2 16,18] [--ntt 16,...] [--precompute F]
   python -m torch.distributed.run --nproc-per-node N tools/sweep.py ...
@@ -50,6 +51,7 @@ def run(lib, pkg=pkg, msm=(16, 18, 20, 22, 24, 26), g2=(16, 18, 20, 22), ntt=(16
     rank = dist.get_rank() if world > 1 else 0
     rng = np.random.default_rng(20261017)
     results = []
+    comm = pkg.multi_gpu.LibComm.from_torch(lib) if world > 1 else None
 
     def out(d):
         if rank == 0:
@@ -85,12 +87,11 @@ def run(lib, pkg=pkg, msm=(16, 18, 20, 22, 24, 26), g2=(16, 18, 20, 22), ntt=(16
             tab = torch.empty((n_loc * precompute, w), dtype=torch.int32, device="cuda")
             lib.msm_precompute_bases(pts.data_ptr(), cfg, g2=is_g2, n=n_loc, out=tab.data_ptr())
             torch.cuda.synchronize()
-        gathered = [torch.empty_like(res) for _ in range(world)] if world > 1 else None
-
         def step():
-            lib.msm(sc.data_ptr(), tab.data_ptr(), cfg, g2=is_g2, results=res.data_ptr(), msm_size=n_loc)
-            if world > 1:
-                dist.all_gather(gathered, res)
+            if comm is not None:  # synchronous: partial sum, all-gather and fold inside the library
+                comm.msm(sc.data_ptr(), tab.data_ptr(), n_loc, cfg, g2=is_g2)
+            else:
+                lib.msm(sc.data_ptr(), tab.data_ptr(), cfg, g2=is_g2, results=res.data_ptr(), msm_size=n_loc)
 
         ms = timed(step, sync=(dist.barrier if world > 1 else None))
         t = torch.tensor([ms], device="cuda")
@@ -131,6 +132,8 @@ def run(lib, pkg=pkg, msm=(16, 18, 20, 22, 24, 26), g2=(16, 18, 20, 22), ntt=(16
              "melem_s": round(batch * n / ms / 1e3, 1), "algorithmic_gb_s": round(batch * n * 64 / ms / 1e6, 1),
              "field_mul_g_s": round(muls / ms / 1e6, 1), "t_mac_s": round(muls * 136 / ms / 1e9, 3)})
         del x, y
+    if comm is not None:
+        comm.close()
     return results
 
 
