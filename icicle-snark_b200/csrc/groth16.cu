@@ -33,6 +33,7 @@
 #include <sys/mman.h>
 #include <sys/stat.h>
 #include <unistd.h>
+#include <chrono>
 #include <vector>
 
 #include "host_math.h"
@@ -183,6 +184,9 @@ struct b200_zkey_cache {
   Fr* qx_slices = nullptr;
   uint8_t *d_all_parts = nullptr, *h_all_parts = nullptr;
   cudaEvent_t ev_slice = nullptr;
+  // B200_SCHED: order of the multiplier-bound phases of one proof (0 = all streams free-running; see commit_enqueue)
+  int sched = 0;
+  cudaEvent_t ev_tok[4] = {nullptr, nullptr, nullptr, nullptr};
 };
 
 namespace b200 {
@@ -251,7 +255,8 @@ namespace b200 {
     cudaStream_t ss[] = {c->s_copy, c->s_g1, c->s_g2, c->s_q};
     for (auto s : ss)
       if (s) cudaStreamDestroy(s);
-    cudaEvent_t es[] = {c->ev_start, c->ev_h2d, c->ev_r1cs, c->ev_ntt, c->ev_g1, c->ev_g2, c->ev_q, c->ev_prev, c->ev_b1};
+    cudaEvent_t es[] = {c->ev_start, c->ev_h2d, c->ev_r1cs, c->ev_ntt, c->ev_g1, c->ev_g2, c->ev_q, c->ev_prev, c->ev_b1,
+                        c->ev_tok[0], c->ev_tok[1], c->ev_tok[2], c->ev_tok[3]};
     for (auto e : es)
       if (e) cudaEventDestroy(e);
     delete c;
@@ -306,8 +311,12 @@ namespace b200 {
         ICICLE_COPY_FAILED);
     }
     if (f == 1) return ICICLE_SUCCESS;
-    eIcicleError e = precompute_enqueue<F>(tmp, true, (int)n, f, plan.c * plan.sets, *out, true, st);
-    cudaFreeAsync(tmp, st);
+    // the tables are built on a second stream so the next section's upload (and the host-side CSR build) overlap them
+    cudaStream_t sp = c->s_q;
+    B200_CUDA(cudaEventRecord(c->ev_b1, st), ICICLE_UNKNOWN_FALLBACK);
+    B200_CUDA(cudaStreamWaitEvent(sp, c->ev_b1, 0), ICICLE_UNKNOWN_FALLBACK);
+    eIcicleError e = precompute_enqueue<F>(tmp, true, (int)n, f, plan.c * plan.sets, *out, true, sp);
+    cudaFreeAsync(tmp, sp);
     return e;
   }
 
@@ -413,11 +422,20 @@ namespace b200 {
     CK(cudaStreamCreateWithPriority(&c->s_q, cudaStreamNonBlocking, use_prio ? prio_hi : prio_lo));
     CK(cudaStreamCreateWithPriority(&c->s_g2, cudaStreamNonBlocking, use_prio && prio_hi + 1 <= prio_lo ? prio_hi + 1 : prio_lo));
     CK(cudaStreamCreateWithPriority(&c->s_g1, cudaStreamNonBlocking, prio_lo));
-    for (cudaEvent_t* e : {&c->ev_prev, &c->ev_b1})
+    for (cudaEvent_t* e : {&c->ev_prev, &c->ev_b1, &c->ev_tok[0], &c->ev_tok[1], &c->ev_tok[2], &c->ev_tok[3]})
       CK(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+    if (const char* se = getenv("B200_SCHED")) c->sched = atoi(se);
     for (cudaEvent_t* e : {&c->ev_start, &c->ev_h2d, &c->ev_r1cs, &c->ev_ntt, &c->ev_g1, &c->ev_g2, &c->ev_q})
       CK(cudaEventCreate(e));
     cudaStream_t st = c->s_copy;
+    // B200_CACHE_TIMING=1: host-clock breakdown of the cold path on stderr
+    const bool timing = getenv("B200_CACHE_TIMING") != nullptr;
+    const auto t_begin = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what) {
+      if (timing)
+        fprintf(stderr, "[icicle_b200] cache build: %-28s +%.3f s\n", what,
+                std::chrono::duration<double>(std::chrono::steady_clock::now() - t_begin).count());
+    };
 
     // ---- base points: this rank's contiguous shard of every section
     // A, B1, B2 and C (padded in front with n_public+1 points at infinity) are all indexed by signal, so the four
@@ -482,6 +500,7 @@ namespace b200 {
     if ((err = upload_points<Fq>(c, sec[8], c->n_public + 1, c->c_lo, c->c_hi, c->planC, &c->pC, st)) != ICICLE_SUCCESS)
       return fail(err);
     if ((err = upload_points<Fq>(c, sec[9], 0, c->h_lo, c->h_hi, c->planH, &c->pH, st)) != ICICLE_SUCCESS) return fail(err);
+    lap("points uploaded, tables queued");
 
     // ---- coefficients -> CSR (record layout: cache.rs:126-166)
     const Section& cs = sec[4];
@@ -515,6 +534,7 @@ namespace b200 {
       col[pos] = sig;
       memcpy(&val[pos], r + 12, 32);
     }
+    lap("CSR built on the host");
     CK(dev_alloc(&c->row_ptr, row_ptr.size(), c));
     CK(dev_alloc(&c->col, col.size(), c));
     CK(dev_alloc(&c->val, val.size(), c));
@@ -553,7 +573,10 @@ namespace b200 {
     CK(dev_alloc(&c->d_scratch_results, (size_t)2 * 96, c));
     CK(cudaHostAlloc((void**)&c->h_results, 4 * 96 + 192, cudaHostAllocDefault));
     CK(cudaGetLastError());
+    lap("everything queued");
     CK(cudaStreamSynchronize(st)); // host vectors go out of scope
+    CK(cudaStreamSynchronize(c->s_q)); // precompute tables
+    lap("device idle");
     CK(cudaEventRecord(c->ev_prev, st));
 #undef CK
     *out = c;
@@ -628,27 +651,50 @@ namespace b200 {
   }
 
   // h = a.b - c over this rank's H shard (a, b, c point at the shard's first element), then the H MSM, on s_q
-  static eIcicleError enqueue_h(b200_zkey_cache* c, const Fr* a, const Fr* b, const Fr* cc)
+  static eIcicleError enqueue_h_combine(b200_zkey_cache* c, const Fr* a, const Fr* b, const Fr* cc)
+  {
+    const uint32_t cnt = c->h_hi - c->h_lo;
+    if (cnt) B200_LAUNCH(quotient_combine_kernel, grid_for(cnt, 256, 8), 256, 0, c->s_q, a, b, cc, cnt, c->d_h + c->h_lo);
+    cudaEventRecord(c->ev_ntt, c->s_q);
+    return ICICLE_SUCCESS;
+  }
+  // the H MSM; with a token its accumulation phase waits for *tok and *tok becomes "H accumulated" (see commit_enqueue)
+  static eIcicleError enqueue_h_msm(b200_zkey_cache* c, cudaEvent_t* tok = nullptr)
   {
     const uint32_t cnt = c->h_hi - c->h_lo;
     if (cnt) {
-      B200_LAUNCH(quotient_combine_kernel, grid_for(cnt, 256, 8), 256, 0, c->s_q, a, b, cc, cnt, c->d_h + c->h_lo);
-      cudaEventRecord(c->ev_ntt, c->s_q);
+      if (tok) {
+        tl_msm_hook.wait_before_acc = *tok;
+        tl_msm_hook.record_after_acc = c->ev_tok[3];
+        *tok = c->ev_tok[3];
+      }
       B200_TRY(msm_enqueue<Fq>(c->planH, c->d_h + c->h_lo, false, c->pH, result_slots(c).h, c->s_q));
-    } else {
-      cudaEventRecord(c->ev_ntt, c->s_q);
     }
     cudaEventRecord(c->ev_q, c->s_q);
     return ICICLE_SUCCESS;
+  }
+  static eIcicleError enqueue_h(b200_zkey_cache* c, const Fr* a, const Fr* b, const Fr* cc)
+  {
+    B200_TRY(enqueue_h_combine(c, a, b, cc));
+    return enqueue_h_msm(c);
   }
 
   // witness-only MSMs (proof_helper.rs:198-206): A, B1, C and B2 take the same scalars over signal-indexed point
   // tables, so ONE digit decomposition + counting sort feeds one G1 accumulate/reduce over three tables (s_g1) and
   // one G2 accumulate/reduce (s_g2)
-  static eIcicleError enqueue_witness_msms(b200_zkey_cache* c)
+  // With a token (B200_SCHED) the accumulation phases run one after the other: the first waits for *tok, each next one
+  // for its predecessor, *tok becomes the last one's completion; g1_first picks the order of the G1 and G2 phases.
+  static eIcicleError enqueue_witness_msms(b200_zkey_cache* c, cudaEvent_t* tok = nullptr, bool g1_first = false)
   {
     ResultSlots r = result_slots(c);
     const Fr* w = c->d_witness;
+    int next_tok = 0;
+    auto chain = [&]() { // arms the hook of the next msm_reduce_enqueue
+      if (!tok) return;
+      tl_msm_hook.wait_before_acc = *tok;
+      tl_msm_hook.record_after_acc = c->ev_tok[next_tok];
+      *tok = c->ev_tok[next_tok++];
+    };
     if (c->a_hi > c->a_lo && c->b_sparse) {
       // sparse B: A and C share the signal-indexed sort (s_g1); B1 and B2 share a second, shorter sort over the
       // gathered witness values of the signals that have a B point (s_g2)
@@ -656,18 +702,26 @@ namespace b200 {
       B200_TRY(msm_sort_enqueue(c->planA, w + c->a_lo, false, &sorted_ac, c->s_g1));
       const G1Affine* ac_tables[2] = {c->pA, c->pC};
       G1Projective* tmp_ac = (G1Projective*)c->d_scratch_results; // A, C contiguous
-      B200_TRY(msm_reduce_enqueue<Fq>(c->planA, sorted_ac, ac_tables, 2, tmp_ac, c->s_g1));
-      cudaMemcpyAsync(r.a, tmp_ac, 96, cudaMemcpyDeviceToDevice, c->s_g1);
-      cudaMemcpyAsync(r.c, tmp_ac + 1, 96, cudaMemcpyDeviceToDevice, c->s_g1);
-      msm_sorted_free(&sorted_ac, c->s_g1);
+      auto enqueue_ac = [&]() -> eIcicleError {
+        chain();
+        B200_TRY(msm_reduce_enqueue<Fq>(c->planA, sorted_ac, ac_tables, 2, tmp_ac, c->s_g1));
+        cudaMemcpyAsync(r.a, tmp_ac, 96, cudaMemcpyDeviceToDevice, c->s_g1);
+        cudaMemcpyAsync(r.c, tmp_ac + 1, 96, cudaMemcpyDeviceToDevice, c->s_g1);
+        msm_sorted_free(&sorted_ac, c->s_g1);
+        return ICICLE_SUCCESS;
+      };
+      if (!tok || g1_first || c->n_b == 0) B200_TRY(enqueue_ac());
       if (c->n_b > 0) {
         B200_LAUNCH(gather_scalars_kernel, grid_for(c->n_b, 256, 8), 256, 0, c->s_g2, w + c->a_lo, c->idxB, c->n_b, c->d_wb);
         B200_TRY(msm_sort_enqueue(c->planB2, c->d_wb, false, &sorted_b, c->s_g2));
         const G1Affine* b1_tables[1] = {c->pB1};
         const G2Affine* b2_tables[1] = {c->pB2};
+        chain();
         B200_TRY(msm_reduce_enqueue<Fq2>(c->planB2, sorted_b, b2_tables, 1, r.b2, c->s_g2));
+        chain();
         B200_TRY(msm_reduce_enqueue<Fq>(c->planB2, sorted_b, b1_tables, 1, r.b1, c->s_g2));
         msm_sorted_free(&sorted_b, c->s_g2);
+        if (tok && !g1_first) B200_TRY(enqueue_ac());
       } else {
         // no signal has a B point: both commitments are the identity
         static const G1Projective id1 = {Fq::zero(), Fq::raw_one(), Fq::zero()};
@@ -683,8 +737,17 @@ namespace b200 {
       cudaStreamWaitEvent(c->s_g2, c->ev_b1, 0);
       const G1Affine* g1_tables[3] = {c->pA, c->pB1, c->pC};
       const G2Affine* g2_tables[1] = {c->pB2};
-      B200_TRY(msm_reduce_enqueue<Fq>(c->planA, sorted, g1_tables, 3, r.a, c->s_g1));
-      B200_TRY(msm_reduce_enqueue<Fq2>(c->planB2, sorted, g2_tables, 1, r.b2, c->s_g2));
+      if (tok && !g1_first) {
+        chain();
+        B200_TRY(msm_reduce_enqueue<Fq2>(c->planB2, sorted, g2_tables, 1, r.b2, c->s_g2));
+        chain();
+        B200_TRY(msm_reduce_enqueue<Fq>(c->planA, sorted, g1_tables, 3, r.a, c->s_g1));
+      } else {
+        chain();
+        B200_TRY(msm_reduce_enqueue<Fq>(c->planA, sorted, g1_tables, 3, r.a, c->s_g1));
+        chain();
+        B200_TRY(msm_reduce_enqueue<Fq2>(c->planB2, sorted, g2_tables, 1, r.b2, c->s_g2));
+      }
       cudaEventRecord(c->ev_g2, c->s_g2);
       cudaStreamWaitEvent(c->s_g1, c->ev_g2, 0); // the sort's scratch is released after both consumers
       msm_sorted_free(&sorted, c->s_g1);
@@ -712,8 +775,20 @@ namespace b200 {
     B200_TRY(enqueue_upload(c, witness, n_witness));
     const uint32_t N = c->domain_size;
     B200_TRY(enqueue_quotient_polys(c, 0, 3, c->d_vec)); // quotient chain + H on the (higher-priority) s_q
-    B200_TRY(enqueue_h(c, c->d_vec + c->h_lo, c->d_vec + N + c->h_lo, c->d_vec + 2 * (size_t)N + c->h_lo));
-    B200_TRY(enqueue_witness_msms(c));
+    if (c->sched == 0) {
+      B200_TRY(enqueue_h(c, c->d_vec + c->h_lo, c->d_vec + N + c->h_lo, c->d_vec + 2 * (size_t)N + c->h_lo));
+      B200_TRY(enqueue_witness_msms(c));
+      return enqueue_join(c);
+    }
+    // B200_SCHED: every phase below saturates the integer multiply pipe on its own, so running them concurrently buys
+    // nothing and makes their latency-bound reduction tails end together.  One after the other instead - the transform
+    // chain first, then (1) G2, G1, H  (2) G1, G2, H  (3) H, G2, G1  (4) H, G1, G2 - while the sorts and the bucket
+    // reductions of the neighbours overlap the running accumulation.
+    B200_TRY(enqueue_h_combine(c, c->d_vec + c->h_lo, c->d_vec + N + c->h_lo, c->d_vec + 2 * (size_t)N + c->h_lo));
+    cudaEvent_t tok = c->ev_ntt;
+    if (c->sched >= 3) B200_TRY(enqueue_h_msm(c, &tok));
+    B200_TRY(enqueue_witness_msms(c, &tok, c->sched == 2 || c->sched == 4));
+    if (c->sched < 3) B200_TRY(enqueue_h_msm(c, &tok));
     return enqueue_join(c);
   }
 

@@ -102,6 +102,13 @@ namespace b200 {
     int g2, nsel, n, windows, c, factor, nbuckets, batched; // batched: rounds of batched-affine accumulation (0 = XYZZ)
     float ms;
   };
+  // Phase hook for callers that schedule several MSMs on different streams (groth16.cu): the NEXT msm_reduce_enqueue issued
+  // by this host thread waits for `wait_before_acc` right before its bucket-accumulation phase (the sort phases stay free
+  // to overlap) and records `record_after_acc` right after it (before the latency-bound bucket reduction).  Consumed on use.
+  struct MsmPhaseHook {
+    cudaEvent_t wait_before_acc = nullptr, record_after_acc = nullptr;
+  };
+  extern thread_local MsmPhaseHook tl_msm_hook;
   extern int g_profile_mode;
   void msm_profile_begin(cudaStream_t st);
   void msm_profile_end(cudaStream_t st, const MsmPlan& plan, int g2, int nsel, int batched);

@@ -10,6 +10,7 @@ namespace b200 {
 
   unsigned long long g_launches = 0;
   int g_profile_mode = 0;
+  thread_local MsmPhaseHook tl_msm_hook;
   static cudaEvent_t g_profile_events[2] = {nullptr, nullptr};
   static std::vector<MsmProfileRec> g_profile_recs;
   static std::mutex g_profile_mu;

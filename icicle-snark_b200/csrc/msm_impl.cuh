@@ -2,6 +2,7 @@
 // Included by msm_g1.cu (F = Fq) and msm_g2.cu (F = Fq2) so the two instantiations compile in parallel.
 #pragma once
 #include "msm.cuh"
+#include "field_inv.cuh"
 
 namespace b200 {
 
@@ -297,6 +298,22 @@ namespace b200 {
   }
 
   // ------------------------------------------------------------------------------------------------
+  // x^-1 through the division-step inversion (field_inv.cuh: ~57 products' worth, mostly on the ALU pipe) instead of
+  // Fermat's ~380 multiplier-bound products; Fq2 by the norm
+  template <class Cfg>
+  __device__ __forceinline__ Fp<Cfg> inverse_fast(const Fp<Cfg>& x)
+  {
+    return inverse_safegcd(x);
+  }
+  __device__ __forceinline__ Fq2 inverse_fast(const Fq2& x)
+  {
+    Fq n = inverse_safegcd(x.c0.sqr() + x.c1.sqr());
+    return {x.c0 * n, (x.c1 * n).neg()};
+  }
+
+  // Table j of point i is 2^(shift*j) P_i: `shift` Jacobian doublings (a = 0: dbl-2009-l, 2M + 5S - the XYZZ doubling the
+  // buckets use costs 9) from the previous, normalised entry, then one inversion per entry.  The cold path of the prover
+  // (cache build) is dominated by this kernel: 12 extra tables x 17 M points at 3200k constraints.
   template <class F>
   __global__ void __launch_bounds__(128)
     msm_precompute_kernel(const Affine<F>* in, bool in_mont, int n, int factor, int shift, Affine<F>* out, bool out_mont)
@@ -304,13 +321,21 @@ namespace b200 {
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
       Affine<F> a = ld_affine(in + i);
       if (!in_mont) a = {F::to_mont(a.x), F::to_mont(a.y)};
-      XYZZ<F> p = XYZZ<F>::from_affine(a);
       for (int j = 0; j < factor; ++j) {
-        if (j) {
-          for (int k = 0; k < shift; ++k)
-            xyzz_dbl_ni(p);
-          a = p.to_affine();
-          p = XYZZ<F>::from_affine(a); // keep ZZ = 1 so later doublings stay cheap to normalise
+        if (j && !a.is_inf()) {
+          F X = a.x, Y = a.y, Z = F::one();
+#pragma unroll 1
+          for (int k = 0; k < shift; ++k) {
+            F A = X.sqr(), B = Y.sqr(), C = B.sqr();
+            F D = ((X + B).sqr() - A - C).dbl();
+            F E = A.dbl() + A;
+            Z = (Y * Z).dbl();
+            X = E.sqr() - D.dbl();
+            Y = E * (D - X) - C.dbl().dbl().dbl();
+          }
+          // Z = 0 only for a point of order two (none on BN254; arbitrary caller data): inverse(0) = 0 -> (0, 0) = infinity
+          F zi = inverse_fast(Z), zi2 = zi.sqr();
+          a = {X * zi2, Y * (zi2 * zi)};
         }
         Affine<F> o = out_mont ? a : Affine<F>{F::from_mont(a.x), F::from_mont(a.y)};
         st_struct(out + (size_t)i * factor + j, o);
@@ -338,6 +363,8 @@ namespace b200 {
     const MsmPlan& plan, const MsmSorted& sorted, const Affine<F>* const* bases_mont, int nsel, Projective<F>* out_std,
     cudaStream_t st)
   {
+    const MsmPhaseHook hook = tl_msm_hook; // consumed whatever happens below
+    tl_msm_hook = MsmPhaseHook();
     if (nsel < 1 || nsel > MSM_MAX_SEL) return ICICLE_INVALID_ARGUMENT;
     MsmDev pl = msm_dev_plan(plan);
     const int nb = plan.nbuckets;
@@ -374,6 +401,7 @@ namespace b200 {
     const unsigned ysel = (unsigned)nsel;
 
     const int ba_rounds = msm_batch_affine_rounds(plan, sizeof(F) > sizeof(Fq));
+    if (hook.wait_before_acc) cudaStreamWaitEvent(st, hook.wait_before_acc, 0);
     msm_profile_begin(st);
     if (ba_rounds) {
       // long buckets: pairwise tree of batched affine additions (msm_batch_affine.cuh), 6-7 products per add
@@ -394,6 +422,7 @@ namespace b200 {
         sorted.item_off, partials, buckets, (uint32_t)nb, (uint32_t)max_items);
     }
     msm_profile_end(st, plan, sizeof(F) > sizeof(Fq) ? 1 : 0, nsel, ba_rounds);
+    if (hook.record_after_acc) cudaEventRecord(hook.record_after_acc, st);
     B200_LAUNCH(
       msm_reduce_chunks_kernel<F>, grid_for((size_t)nsets * chunks_per_set, 128, 16), 128, 0, st, pl, nsel, sorted.offsets, buckets,
       chunk_sums, chunk_runs, sum_stride);
@@ -448,6 +477,144 @@ namespace b200 {
     }
   }
 
+  // sum of k partial results (boundary layout: homogeneous projective, standard form) -> out; one thread
+  template <class F>
+  __global__ void msm_combine_chunks_kernel(const Projective<F>* parts, int k, Projective<F>* out)
+  {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    XYZZ<F> acc = XYZZ<F>::inf();
+    for (int i = 0; i < k; ++i) {
+      Projective<F> p = ld_struct(parts + i);
+      Projective<F> m = {F::to_mont(p.x), F::to_mont(p.y), F::to_mont(p.z)};
+      xyzz_add_ni(acc, xyzz_from_projective(m));
+    }
+    Projective<F> r = acc.to_projective();
+    Projective<F> o = {F::from_mont(r.x), F::from_mont(r.y), F::from_mont(r.z)};
+    st_struct(out, o);
+  }
+
+  // Largest number of points one Pippenger pass may take: 32-bit entry positions (n * windows < 2^32), 31-bit table
+  // indices (n * f < 2^31), and the device memory the pass needs (staging of host operands, the sort scratch, the
+  // Montgomery copy of the points) within 70 % of what is free now.  B200_MSM_CHUNK=<points> forces a smaller chunk
+  // (tests).  The reference splits for the same reasons (cuda_msm.cuh:1130-1237 multi-chunk, :1239-1394 on memory).
+  inline size_t msm_chunk_points(const MsmPlan& full, int f, size_t affine_bytes, bool host_scalars, bool host_points, bool mont_copy)
+  {
+    size_t lim = ((1ull << 32) - 1) / (size_t)full.windows;
+    const size_t lim_f = ((1ull << 31) - 1) / (size_t)f;
+    if (lim_f < lim) lim = lim_f;
+    size_t per_point = (size_t)full.windows * 4 * 2                    // digits + entries
+                       + (size_t)full.windows * 2 * sizeof(MsmItem) / (size_t)full.item_cap + 1;
+    if (host_scalars) per_point += 2 * 32;                             // double-buffered staging
+    if (host_points) per_point += 2 * affine_bytes * (size_t)f;
+    if (mont_copy) per_point += affine_bytes * (size_t)f;
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
+      const size_t fixed = (size_t)full.nbuckets * (4 * 8 + 2 * sizeof(MsmItem) + 3 * 2 * affine_bytes); // offsets, items, buckets
+      const size_t budget = (size_t)(0.7 * (double)free_b);
+      const size_t by_mem = budget > fixed ? (budget - fixed) / per_point : 1;
+      if (by_mem < lim) lim = by_mem;
+    }
+    if (const char* e = getenv("B200_MSM_CHUNK")) {
+      const long long v = atoll(e);
+      if (v > 0 && (size_t)v < lim) lim = (size_t)v;
+    }
+    return lim < 1 ? 1 : lim;
+  }
+
+  // One MSM larger than a single pass may take (msm_chunk_points) or with host-resident operands that should not be
+  // staged whole: K passes over contiguous chunks, host operands double-buffered on a copy stream so chunk k+1 crosses
+  // PCIe while chunk k is computed, partial sums added by one small kernel.  Every chunk uses the full problem's window
+  // width so a precomputed table (built for that width) stays valid.
+  template <class F>
+  eIcicleError msm_chunked(
+    const MsmPlan& full, const Fr* scalars, bool scalars_dev, const Affine<F>* bases, bool bases_dev, size_t n, size_t chunk,
+    const MSMConfig* cfg, int bitsize, bool g2, Projective<F>* out_dev, cudaStream_t st)
+  {
+    const int f = full.stride;
+    const int K = (int)((n + chunk - 1) / chunk);
+    const bool mont_copy = !cfg->are_points_montgomery_form;
+    cudaStream_t cs = nullptr;
+    cudaEvent_t copied[2] = {nullptr, nullptr}, consumed[2] = {nullptr, nullptr};
+    Fr* sbuf[2] = {nullptr, nullptr};
+    Affine<F>* pbuf[2] = {nullptr, nullptr};
+    Affine<F>* mont_tmp = nullptr;
+    Projective<F>* parts = nullptr;
+    eIcicleError err = ICICLE_SUCCESS;
+    auto ck = [&](cudaError_t e, eIcicleError code) {
+      if (e != cudaSuccess && err == ICICLE_SUCCESS) {
+        fprintf(stderr, "[icicle_b200] chunked msm: %s\n", cudaGetErrorString(e));
+        err = code;
+      }
+      return e == cudaSuccess;
+    };
+    const bool staged = !scalars_dev || !bases_dev;
+    if (staged) {
+      ck(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking), ICICLE_STREAM_CREATION_FAILED);
+      for (int i = 0; i < 2 && err == ICICLE_SUCCESS; ++i) {
+        ck(cudaEventCreateWithFlags(&copied[i], cudaEventDisableTiming), ICICLE_UNKNOWN_FALLBACK);
+        ck(cudaEventCreateWithFlags(&consumed[i], cudaEventDisableTiming), ICICLE_UNKNOWN_FALLBACK);
+        if (!scalars_dev) ck(cudaMallocAsync((void**)&sbuf[i], chunk * sizeof(Fr), st), ICICLE_ALLOCATION_FAILED);
+        if (!bases_dev) ck(cudaMallocAsync((void**)&pbuf[i], chunk * f * sizeof(Affine<F>), st), ICICLE_ALLOCATION_FAILED);
+      }
+      if (err == ICICLE_SUCCESS) { // the copy stream may touch the buffers once they exist in st's order
+        ck(cudaEventRecord(consumed[0], st), ICICLE_UNKNOWN_FALLBACK);
+        ck(cudaEventRecord(consumed[1], st), ICICLE_UNKNOWN_FALLBACK);
+      }
+    }
+    if (err == ICICLE_SUCCESS && mont_copy) ck(cudaMallocAsync((void**)&mont_tmp, chunk * f * sizeof(Affine<F>), st), ICICLE_ALLOCATION_FAILED);
+    if (err == ICICLE_SUCCESS) ck(cudaMallocAsync((void**)&parts, (size_t)K * sizeof(Projective<F>), st), ICICLE_ALLOCATION_FAILED);
+    auto stage = [&](int k) { // enqueue the host->device copies of chunk k on the copy stream
+      const size_t lo = (size_t)k * chunk, cn = std::min(chunk, n - lo);
+      const int b = k & 1;
+      ck(cudaStreamWaitEvent(cs, consumed[b], 0), ICICLE_UNKNOWN_FALLBACK);
+      if (!scalars_dev) ck(cudaMemcpyAsync(sbuf[b], scalars + lo, cn * sizeof(Fr), cudaMemcpyHostToDevice, cs), ICICLE_COPY_FAILED);
+      if (!bases_dev)
+        ck(cudaMemcpyAsync(pbuf[b], bases + lo * f, cn * f * sizeof(Affine<F>), cudaMemcpyHostToDevice, cs), ICICLE_COPY_FAILED);
+      ck(cudaEventRecord(copied[b], cs), ICICLE_UNKNOWN_FALLBACK);
+    };
+    if (err == ICICLE_SUCCESS && staged) stage(0);
+    for (int k = 0; k < K && err == ICICLE_SUCCESS; ++k) {
+      const size_t lo = (size_t)k * chunk, cn = std::min(chunk, n - lo);
+      const int b = k & 1;
+      if (staged) {
+        if (k + 1 < K) stage(k + 1);
+        ck(cudaStreamWaitEvent(st, copied[b], 0), ICICLE_UNKNOWN_FALLBACK);
+      }
+      const Fr* sc = scalars_dev ? scalars + lo : sbuf[b];
+      const Affine<F>* pts = bases_dev ? bases + lo * f : pbuf[b];
+      if (mont_copy && err == ICICLE_SUCCESS) {
+        B200_LAUNCH(affine_to_mont_kernel<F>, grid_for(cn * f, 256, 8), 256, 0, st, pts, cn * f, mont_tmp);
+        pts = mont_tmp;
+      }
+      MsmPlan plan = make_msm_plan((int)cn, full.c, bitsize, f, g2);
+      if (err == ICICLE_SUCCESS) err = msm_enqueue<F>(plan, sc, cfg->are_scalars_montgomery_form, pts, parts + k, st);
+      if (staged) ck(cudaEventRecord(consumed[b], st), ICICLE_UNKNOWN_FALLBACK);
+    }
+    if (err == ICICLE_SUCCESS) {
+      B200_LAUNCH(msm_combine_chunks_kernel<F>, 1, 32, 0, st, parts, K, out_dev);
+      ck(cudaGetLastError(), ICICLE_UNKNOWN_FALLBACK);
+    }
+    for (int i = 0; i < 2; ++i) {
+      if (sbuf[i]) cudaFreeAsync(sbuf[i], st);
+      if (pbuf[i]) cudaFreeAsync(pbuf[i], st);
+    }
+    if (mont_tmp) cudaFreeAsync(mont_tmp, st);
+    if (parts) cudaFreeAsync(parts, st);
+    if (staged) {
+      // the copy stream and its events must outlive the work that references them
+      if (err != ICICLE_SUCCESS) cudaStreamSynchronize(st);
+      if (cs) {
+        cudaStreamSynchronize(cs);
+        cudaStreamDestroy(cs);
+      }
+      for (int i = 0; i < 2; ++i) {
+        if (copied[i]) cudaEventDestroy(copied[i]);
+        if (consumed[i]) cudaEventDestroy(consumed[i]);
+      }
+    }
+    return err;
+  }
+
   template <class F>
   eIcicleError msm_api(const void* scalars_v, const void* bases_v, int msm_size, const MSMConfig* cfg, void* results_v, bool g2)
   {
@@ -459,7 +626,26 @@ namespace b200 {
     const int f = cfg->precompute_factor > 1 ? cfg->precompute_factor : 1;
     const int bitsize = cfg->bitsize > 0 ? cfg->bitsize : 254;
     const bool shared = cfg->are_points_shared_in_batch || batch == 1;
-    if ((size_t)msm_size * f >= (1ull << 31)) return ICICLE_INVALID_ARGUMENT;
+    const bool s_dev = is_device_ptr(scalars_v, cfg->are_scalars_on_device);
+    const bool p_dev = is_device_ptr(bases_v, cfg->are_points_on_device);
+
+    // one pass when it fits (32-bit entry positions, table indices, device memory); otherwise chunks
+    MsmPlan plan = make_msm_plan(msm_size > 0 ? msm_size : 1, cfg->c, bitsize, f, g2);
+    const size_t chunk = msm_size > 0 ? msm_chunk_points(plan, f, sizeof(Affine<F>), !s_dev, !p_dev, !cfg->are_points_montgomery_form) : 1;
+    if (msm_size > 0 && chunk < (size_t)msm_size) {
+      StagedOut O;
+      B200_TRY(O.init(results_v, (size_t)batch * sizeof(Projective<F>), cfg->are_results_on_device, st));
+      eIcicleError err = ICICLE_SUCCESS;
+      for (int b = 0; b < batch && err == ICICLE_SUCCESS; ++b)
+        err = msm_chunked<F>(
+          plan, (const Fr*)scalars_v + (size_t)b * msm_size, s_dev,
+          (const Affine<F>*)bases_v + (shared ? 0 : (size_t)b * msm_size * f), p_dev, (size_t)msm_size, chunk, cfg, bitsize, g2,
+          (Projective<F>*)O.dev + b, st);
+      if (err == ICICLE_SUCCESS) err = O.finish(st);
+      if (err != ICICLE_SUCCESS) return err;
+      if (!cfg->is_async) B200_CUDA(cudaStreamSynchronize(st), ICICLE_SYNCHRONIZATION_FAILED);
+      return ICICLE_SUCCESS;
+    }
 
     const size_t n_scalars = (size_t)msm_size * batch;
     const size_t n_points = (size_t)msm_size * f * (shared ? 1 : batch);
@@ -485,8 +671,6 @@ namespace b200 {
           err = ICICLE_COPY_FAILED;
       cudaStreamSynchronize(st); // `id` is a stack temporary
     } else {
-      MsmPlan plan = make_msm_plan(msm_size, cfg->c, bitsize, f, g2);
-      if (plan.entries() >= (1ull << 32)) err = ICICLE_INVALID_ARGUMENT; // entry positions are 32-bit
       for (int b = 0; b < batch && err == ICICLE_SUCCESS; ++b) {
         err = msm_enqueue<F>(
           plan, (const Fr*)S.dev + (size_t)b * msm_size, cfg->are_scalars_montgomery_form,

@@ -28,8 +28,12 @@ class ZKeyCache:
     def __init__(self, lib, zkey_bytes, precompute=1, rank=0, world=1):
         self.lib = lib
         self.handle = C.c_void_p()
-        buf = (C.c_ubyte * len(zkey_bytes)).from_buffer_copy(zkey_bytes) if not isinstance(zkey_bytes, mmap.mmap) else \
-            (C.c_ubyte * len(zkey_bytes)).from_buffer(zkey_bytes)
+        if isinstance(zkey_bytes, bytes):
+            buf = C.c_char_p(zkey_bytes)  # the object's own buffer: no copy of a gigabyte-sized file
+        elif isinstance(zkey_bytes, mmap.mmap):
+            buf = (C.c_ubyte * len(zkey_bytes)).from_buffer(zkey_bytes)
+        else:
+            buf = (C.c_ubyte * len(zkey_bytes)).from_buffer_copy(zkey_bytes)
         check(lib.dll.b200_zkey_cache_create_sharded(buf, C.c_size_t(len(zkey_bytes)), C.c_int(precompute), C.c_int(rank),
                                                      C.c_int(world), C.byref(self.handle)), "b200_zkey_cache_create")
         nv, npub, dom, ncoef, dbytes = C.c_uint32(), C.c_uint32(), C.c_uint32(), C.c_uint64(), C.c_uint64()

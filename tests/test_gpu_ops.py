@@ -237,6 +237,48 @@ def test_msm_precompute_batch(gpu, ref, rng, shared):
         assert affine_eq(ref, got[b], want[b]), b
 
 
+@pytest.mark.parametrize("g2", [False, True])
+@pytest.mark.parametrize("chunk", [1, 700, 4096])
+def test_msm_chunked_passes_match_reference(gpu, ref, rng, monkeypatch, g2, chunk):
+    """Oversize / host-resident inputs take several Pippenger passes (msm_chunked; the reference's multi-chunk path,
+    cuda_msm.cuh:1130-1237).  B200_MSM_CHUNK forces the split at test sizes: ragged last chunk, one-point chunks, host
+    operands (double-buffered staging) and device operands, standard-form points (per-chunk Montgomery copy)."""
+    n = 5 if chunk == 1 else 3001
+    sc, pts = _msm_inputs(ref, rng, n, g2=g2)
+    want = ref.msm(sc, pts, g2=g2)
+    monkeypatch.setenv("B200_MSM_CHUNK", str(chunk))
+    got = gpu.msm(sc, pts, g2=g2)  # host operands
+    assert affine_eq(ref, got[0], want[0], g2=g2)
+    ds, dp = gpu.malloc(sc.nbytes), gpu.malloc(pts.nbytes)
+    try:
+        gpu.copy_to_device(ds, sc)
+        gpu.copy_to_device(dp, pts)
+        cfg = B.MSMConfig.default()
+        cfg.are_scalars_on_device = cfg.are_points_on_device = True
+        got = gpu.msm(ds, dp, cfg, g2=g2, msm_size=n)  # device operands, host result
+        assert affine_eq(ref, got[0], want[0], g2=g2)
+    finally:
+        gpu.free(ds)
+        gpu.free(dp)
+
+
+def test_msm_chunked_with_precompute_and_batch(gpu, ref, rng, monkeypatch):
+    """A precomputed table is built for the FULL problem's window width; every chunk must keep that width."""
+    n, batch, f = 2500, 2, 8
+    cfg = B.MSMConfig.default()
+    cfg.batch_size, cfg.are_points_shared_in_batch, cfg.precompute_factor = batch, True, f
+    sc, _ = rand_scalars(rng, n * batch)
+    pts = ref.generate_affine_points(n)
+    plain = B.MSMConfig.default()
+    plain.batch_size, plain.are_points_shared_in_batch = batch, True
+    want = ref.msm(sc, pts, plain)
+    table = gpu.msm_precompute_bases(pts, cfg)
+    monkeypatch.setenv("B200_MSM_CHUNK", "999")
+    got = gpu.msm(sc, table, cfg, msm_size=n)
+    for b in range(batch):
+        assert affine_eq(ref, got[b], want[b]), b
+
+
 def test_division_step_inverse_on_device(gpu):
     # csrc/field_inv.cuh on the GPU: 2^17 inversions per field against x * x^-1 == 1 (and Fermat on the first few)
     f = pkg.tools_lib().b200_inv_check
