@@ -573,7 +573,7 @@ def main():
         "warmup": args.warmup, "ms_per_step": ms_dev, "higher_is_better": False, "scaling": "strong", "vs_baseline": None,
         "dtype": "u32x8 (254-bit modular integers)", "data": "synthetic",
         "config": {"workload": f"ComplexCircuit({n},{n}) Groth16 prove, warm ZKeyCache", "n_vars": cache.n_vars,
-                   "domain_size": cache.domain_size, "precompute_factor": args.precompute, "parallelism": f"msm-shard{world}" + ("+quotient-split" if (qx is not None or comm is not None) else "") + ("+in-library-nccl" if comm is not None else "") + (f"+shard-skew{skew:g}" if skew > 0 else ""),
+                   "domain_size": cache.domain_size, "precompute_factor": args.precompute, "parallelism": f"msm-shard{world}" + (("+line-plan" if lib.dll.b200_shard_plan_mode(world) == 1 else "+uniform-plan") if world > 1 else "") + ("+quotient-split" if (qx is not None or comm is not None) else "") + ("+in-library-nccl" if comm is not None else "") + (f"+shard-skew{skew:g}" if skew > 0 else ""),
                    "blinding": "fixed non-trivial r, s", "l2": "256 MiB flush between timed iterations",
                    "timing": "host clock around the synchronous C-ABI call + cuda sync + barrier, max over ranks"},
         "e2e": {"value": ms_e2e, "unit": "ms", "h2d_bytes_per_step": nw * 32, "d2h_bytes_per_step": 576 if world == 1 else 576 * world,

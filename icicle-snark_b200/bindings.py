@@ -153,7 +153,7 @@ b200_zkey_cache_create_sharded b200_groth16_commit_partials b200_groth16_finish 
 b200_groth16_commit_begin b200_groth16_commit_end b200_zkey_cache_h_range b200_proof_to_json b200_zkey_cache_b_points
 b200_version b200_launch_count b200_fixed_base_mul b200_profile_accumulate b200_profile_records
 b200_groth16_verify b200_groth16_verify_files b200_msm_plan_info b200_shard_range
-b200_comm_unique_id b200_comm_create b200_comm_destroy b200_comm_info b200_groth16_prove_sharded b200_msm_sharded
+b200_shard_plan b200_shard_plan_mode b200_zkey_cache_ranges b200_comm_unique_id b200_comm_create b200_comm_destroy b200_comm_info b200_groth16_prove_sharded b200_msm_sharded
 """.split()
 
 

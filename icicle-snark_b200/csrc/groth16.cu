@@ -34,6 +34,7 @@
 #include <sys/stat.h>
 #include <unistd.h>
 #include <chrono>
+#include <cmath>
 #include <vector>
 
 #include "host_math.h"
@@ -154,17 +155,35 @@ struct b200_zkey_cache {
   // verification-key points needed by the epilogue (Montgomery, as stored: zkey.rs:61-69)
   G1Affine alpha1, beta1, delta1;
   G2Affine beta2, delta2;
-  // shard [lo,hi) of every base-point section held by this rank
-  uint32_t a_lo = 0, a_hi = 0, c_lo = 0, c_hi = 0, h_lo = 0, h_hi = 0;
-  G1Affine *pA = nullptr, *pB1 = nullptr, *pC = nullptr, *pH = nullptr;
-  G2Affine* pB2 = nullptr;
-  MsmPlan planA, planC, planH, planB2;
+  // this rank's [lo,hi) of every base-point section (b200_shard_plan): 0 = H, 1 = A, 2 = B1, 3 = C, 4 = B2
+  uint32_t sec_lo[5] = {0, 0, 0, 0, 0}, sec_hi[5] = {0, 0, 0, 0, 0};
+  uint32_t h_lo = 0, h_hi = 0; // == section 0
+  int plan_mode = 0;           // shard_plan mode and skew this cache was cut with
+  double plan_skew = 0;
+  uint32_t w_lo = 0, w_hi = 0; // span of the witness this rank's MSMs read
+  G1Affine* pH = nullptr;
+  MsmPlan planH;
+  // The witness MSMs (A, B1, C in G1, B2 in G2) take the same scalars over signal-indexed tables: sections that cover
+  // the same signal range on this rank form a GROUP with one digit decomposition + counting sort feeding one fused G1
+  // accumulate/reduce over its G1 tables and one G2 accumulate/reduce.  One GPU: a single group {A, B1, C, B2}.
   // B1/B2 columns that are points at infinity (signals absent from every B row: the norm in circom circuits) are
-  // dropped at build time when they are >= 1/8 of the shard: idxB lists the surviving signals (relative to a_lo)
-  uint32_t* idxB = nullptr;
-  uint32_t n_b = 0;   // number of B points kept (== a_hi - a_lo when dense)
-  bool b_sparse = false;
-  Fr* d_wb = nullptr; // gathered witness values for the sparse B MSMs
+  // dropped at build time when they are >= 1/8 of the range: such a COMPACT group keeps `idx` (surviving signals
+  // relative to lo) and gathers their witness values into d_w before its sort.
+  struct WGroup {
+    uint32_t lo = 0, hi = 0, n = 0; // signal range; points per table (hi - lo, or the kept count when compact)
+    bool compact = false;
+    uint32_t* idx = nullptr;
+    Fr* d_w = nullptr;
+    MsmPlan plan;
+    int n_g1 = 0;
+    G1Affine* g1[3] = {nullptr, nullptr, nullptr};
+    int g1_slot[3] = {0, 0, 0}; // result slot of each table: 0 = A, 1 = B1, 2 = C
+    G2Affine* g2 = nullptr;
+    G1Projective* d_out = nullptr; // results of the fused G1 launch before they move to their slots
+    cudaEvent_t ev_sort = nullptr, ev_done = nullptr;
+  };
+  std::vector<WGroup> groups;
+  uint32_t n_b = 0, b_total = 0; // B1 points kept / B1 range size on this rank (b200_zkey_cache_b_points)
   // R1CS in CSR over rows [A rows 0..N) | B rows 0..N)]
   uint32_t *row_ptr = nullptr, *col = nullptr;
   Fr* val = nullptr;
@@ -172,21 +191,18 @@ struct b200_zkey_cache {
   // per-proof workspace
   Fr *d_witness = nullptr, *d_vec = nullptr, *d_h = nullptr;
   uint8_t* d_results = nullptr; // 4 x G1 projective + 1 x G2 projective
-  uint8_t* d_scratch_results = nullptr; // 2 x G1 projective (A, C of the sparse-B path)
   uint8_t* h_results = nullptr; // pinned
-  cudaStream_t s_copy = nullptr, s_g1 = nullptr, s_g2 = nullptr, s_q = nullptr;
+  cudaStream_t s_copy = nullptr, s_g1 = nullptr, s_g2 = nullptr, s_g3 = nullptr, s_q = nullptr;
   cudaEvent_t ev_start = nullptr, ev_h2d = nullptr, ev_r1cs = nullptr, ev_ntt = nullptr, ev_g1 = nullptr,
-              ev_g2 = nullptr, ev_q = nullptr, ev_prev = nullptr, ev_b1 = nullptr;
+              ev_g2 = nullptr, ev_q = nullptr, ev_prev = nullptr, ev_b1 = nullptr, ev_free = nullptr;
   std::mutex mu;
   bool in_flight = false; // commit_begin succeeded and holds `mu` until commit_end
   // in-library exchange of the sharded prover (b200_groth16_prove_sharded): this rank's slice of the three transformed
   // polynomials, every rank's partial sums
   Fr* qx_slices = nullptr;
   uint8_t *d_all_parts = nullptr, *h_all_parts = nullptr;
-  cudaEvent_t ev_slice = nullptr;
-  // B200_SCHED: order of the multiplier-bound phases of one proof (0 = all streams free-running; see commit_enqueue)
-  int sched = 0;
-  cudaEvent_t ev_tok[4] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev_slice = nullptr, ev_xch = nullptr;
+  size_t wit_slice = 0; // d_witness holds world * wit_slice elements (>= n_vars): in-place all-gather of the uploaded slices
 };
 
 namespace b200 {
@@ -241,22 +257,119 @@ namespace b200 {
     if (*hi < *lo) *hi = *lo;
   }
 
+  // ---- which part of which base-point section a rank holds; sections: 0 = H, 1 = A, 2 = B1, 3 = C, 4 = B2
+  // mode 0 ("uniform"): every section cut into `world` contiguous ranges - H equally, the four signal-indexed sections
+  //   with the polynomial owners' skew (shard_skewed).  Every rank runs five small MSMs.
+  // mode 1 ("line"): the five sections laid end to end, weighted by their cost per point (G1 = 1, G2 = w2), with the
+  //   quotient-polynomial transforms charged to their owners (w_ntt * N point-equivalents per polynomial), cut into
+  //   `world` pieces of equal cost (B200_PLAN_W2 / B200_PLAN_WH / B200_PLAN_WNTT override the fitted weights).  A rank holds one or two LARGE pieces (whole tables where possible): it keeps the
+  //   wide windows of the single-GPU plan (13 digits per scalar instead of 15 at 3200k constraints on 8 GPUs) and runs two
+  //   or three bucket reductions instead of five.  Cuts that fall within 4 % of a section edge snap to the edge.
+  struct ShardPlan {
+    uint32_t lo[5], hi[5];
+  };
+  // Default cut: B200_SHARD_PLAN = uniform | line when set; otherwise what measured faster at 3200k constraints on B200s
+  // (ms per proof, line vs uniform: 2 GPUs 30.5 vs 31.0, 4 GPUs 18.4 vs 18.0, 8 GPUs 10.2 vs 10.5 - profiles/r02_multi_gpu.md):
+  // few ranks hold whole tables under the line cut and keep the shared sort of equal ranges, many ranks gain from the
+  // wide windows; in between the unfused pieces of a rank (one sort each) cost more than the windows save.
+  static int plan_mode_default(int world)
+  {
+    if (world < 2) return 0;
+    const char* e = getenv("B200_SHARD_PLAN");
+    if (!e || !*e) return (world == 2 || world >= 6) ? 1 : 0;
+    return (e[0] == '0' || e[0] == 'u' || e[0] == 'U') ? 0 : 1;
+  }
+  static double env_double(const char* name, double dflt)
+  {
+    const char* e = getenv(name);
+    return (e && *e) ? atof(e) : dflt;
+  }
+  static ShardPlan shard_plan(uint32_t n_vars, uint32_t N, int rank, int world, int mode, double skew)
+  {
+    ShardPlan sp;
+    if (mode == 0 || world < 2 || world > 64) {
+      shard(N, rank, world, &sp.lo[0], &sp.hi[0]);
+      uint32_t lo, hi;
+      shard_skewed(n_vars, rank, world, skew, &lo, &hi);
+      for (int k = 1; k < 5; ++k) {
+        sp.lo[k] = lo;
+        sp.hi[k] = hi;
+      }
+      return sp;
+    }
+    // fitted on B200 at 3200k constraints (tools/shard_probe.py at 2, 4 and 8 ranks): relative to a point of a fused G1
+    // table, a G2 point costs 3.0 (batched affine rounds plus the longer latency-bound reduction tail of a G2 piece), an
+    // H point 1.1 (its sort cannot start before the transforms end), one polynomial's iNTT + NTT 0.24 N points
+    const double w2 = env_double("B200_PLAN_W2", 3.0), w_h = env_double("B200_PLAN_WH", 1.1), w_ntt = env_double("B200_PLAN_WNTT", 0.24);
+    const double wt[5] = {w_h > 0.1 ? w_h : 1.1, 1.0, 1.0, 1.0, w2 > 0.1 ? w2 : 3.0};
+    const uint32_t cnt[5] = {N, n_vars, n_vars, n_vars, n_vars};
+    double len[5], total = 0;
+    for (int k = 0; k < 5; ++k) {
+      len[k] = cnt[k] * wt[k];
+      total += len[k];
+    }
+    const double ntt = w_ntt * (double)N;
+    const double target = (total + 3 * ntt) / world;
+    double share[64], ssum = 0;
+    for (int r = 0; r < world; ++r) {
+      share[r] = target - ntt * polys_owned(r, world);
+      if (share[r] < 0) share[r] = 0;
+      ssum += share[r];
+    }
+    auto cut = [&](int r) { // position of the boundary in front of rank r on the weighted line
+      if (r <= 0) return 0.0;
+      if (r >= world) return total;
+      double acc = 0;
+      for (int q = 0; q < r; ++q)
+        acc += share[q];
+      double x = acc * (total / ssum), off = 0;
+      for (int k = 0; k < 5; ++k) { // snap to a nearby section edge
+        if (fabs(x - off) < 0.04 * len[k]) return off;
+        if (fabs(x - (off + len[k])) < 0.04 * len[k]) return off + len[k];
+        off += len[k];
+      }
+      return x;
+    };
+    const double b = cut(rank), e = cut(rank + 1);
+    double off = 0;
+    for (int k = 0; k < 5; ++k) {
+      auto to_pt = [&](double x) {
+        double y = (x - off) / wt[k];
+        if (y <= 0) return (uint32_t)0;
+        if (y >= (double)cnt[k]) return cnt[k];
+        return (uint32_t)(y + 0.5);
+      };
+      sp.lo[k] = to_pt(b);
+      sp.hi[k] = to_pt(e);
+      if (sp.hi[k] < sp.lo[k]) sp.hi[k] = sp.lo[k];
+      off += len[k];
+    }
+    return sp;
+  }
+
   static void cache_free(b200_zkey_cache* c)
   {
     if (!c) return;
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
-    void* ptrs[] = {c->idxB, c->d_wb, c->pA, c->pB1, c->pC, c->pH, c->pB2, c->row_ptr, c->col, c->val, c->keys, c->d_witness, c->d_vec, c->d_h, c->d_results, c->d_scratch_results, c->qx_slices, c->d_all_parts};
+    void* ptrs[] = {c->pH, c->row_ptr, c->col, c->val, c->keys, c->d_witness, c->d_vec, c->d_h, c->d_results, c->qx_slices, c->d_all_parts};
     for (void* p : ptrs)
       if (p) cudaFree(p);
+    for (auto& g : c->groups)
+    {
+      for (void* p : {(void*)g.idx, (void*)g.d_w, (void*)g.g1[0], (void*)g.g1[1], (void*)g.g1[2], (void*)g.g2, (void*)g.d_out})
+        if (p) cudaFree(p);
+      if (g.ev_sort) cudaEventDestroy(g.ev_sort);
+      if (g.ev_done) cudaEventDestroy(g.ev_done);
+    }
     if (c->h_results) cudaFreeHost(c->h_results);
     if (c->h_all_parts) cudaFreeHost(c->h_all_parts);
     if (c->ev_slice) cudaEventDestroy(c->ev_slice);
-    cudaStream_t ss[] = {c->s_copy, c->s_g1, c->s_g2, c->s_q};
+    if (c->ev_xch) cudaEventDestroy(c->ev_xch);
+    cudaStream_t ss[] = {c->s_copy, c->s_g1, c->s_g2, c->s_g3, c->s_q};
     for (auto s : ss)
       if (s) cudaStreamDestroy(s);
-    cudaEvent_t es[] = {c->ev_start, c->ev_h2d, c->ev_r1cs, c->ev_ntt, c->ev_g1, c->ev_g2, c->ev_q, c->ev_prev, c->ev_b1,
-                        c->ev_tok[0], c->ev_tok[1], c->ev_tok[2], c->ev_tok[3]};
+    cudaEvent_t es[] = {c->ev_start, c->ev_h2d, c->ev_r1cs, c->ev_ntt, c->ev_g1, c->ev_g2, c->ev_q, c->ev_prev, c->ev_b1, c->ev_free};
     for (auto e : es)
       if (e) cudaEventDestroy(e);
     delete c;
@@ -422,9 +535,9 @@ namespace b200 {
     CK(cudaStreamCreateWithPriority(&c->s_q, cudaStreamNonBlocking, use_prio ? prio_hi : prio_lo));
     CK(cudaStreamCreateWithPriority(&c->s_g2, cudaStreamNonBlocking, use_prio && prio_hi + 1 <= prio_lo ? prio_hi + 1 : prio_lo));
     CK(cudaStreamCreateWithPriority(&c->s_g1, cudaStreamNonBlocking, prio_lo));
-    for (cudaEvent_t* e : {&c->ev_prev, &c->ev_b1, &c->ev_tok[0], &c->ev_tok[1], &c->ev_tok[2], &c->ev_tok[3]})
+    CK(cudaStreamCreateWithPriority(&c->s_g3, cudaStreamNonBlocking, prio_lo));
+    for (cudaEvent_t* e : {&c->ev_prev, &c->ev_b1, &c->ev_free})
       CK(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
-    if (const char* se = getenv("B200_SCHED")) c->sched = atoi(se);
     for (cudaEvent_t* e : {&c->ev_start, &c->ev_h2d, &c->ev_r1cs, &c->ev_ntt, &c->ev_g1, &c->ev_g2, &c->ev_q})
       CK(cudaEventCreate(e));
     cudaStream_t st = c->s_copy;
@@ -437,15 +550,29 @@ namespace b200 {
                 std::chrono::duration<double>(std::chrono::steady_clock::now() - t_begin).count());
     };
 
-    // ---- base points: this rank's contiguous shard of every section
-    // A, B1, B2 and C (padded in front with n_public+1 points at infinity) are all indexed by signal, so the four
-    // witness MSMs share one shard range, one plan and one sort
-    // B200_SHARD_SKEW (set by a caller that splits the quotient chain, see shard_skewed): every rank must use the same value
+    // ---- base points: this rank's part of every section (shard_plan)
+    // B200_SHARD_SKEW (uniform plan; set by a caller that splits the quotient chain, see shard_skewed) and B200_SHARD_PLAN /
+    // B200_PLAN_W2 / B200_PLAN_WNTT: every rank must see the same values
     const char* sk_env = getenv("B200_SHARD_SKEW");
-    shard_skewed(c->n_vars, rank, world, sk_env ? atof(sk_env) : 0.0, &c->a_lo, &c->a_hi);
-    c->c_lo = c->a_lo;
-    c->c_hi = c->a_hi;
-    shard(N, rank, world, &c->h_lo, &c->h_hi);
+    {
+      c->plan_mode = plan_mode_default(world);
+      c->plan_skew = sk_env ? atof(sk_env) : 0.0;
+      ShardPlan sp = shard_plan(c->n_vars, N, rank, world, c->plan_mode, c->plan_skew);
+      for (int k = 0; k < 5; ++k) {
+        c->sec_lo[k] = sp.lo[k];
+        c->sec_hi[k] = sp.hi[k];
+      }
+      c->h_lo = sp.lo[0];
+      c->h_hi = sp.hi[0];
+      c->w_lo = c->n_vars;
+      c->w_hi = 0;
+      for (int k = 1; k < 5; ++k)
+        if (sp.hi[k] > sp.lo[k]) {
+          c->w_lo = std::min(c->w_lo, sp.lo[k]);
+          c->w_hi = std::max(c->w_hi, sp.hi[k]);
+        }
+      if (c->w_hi <= c->w_lo) c->w_lo = c->w_hi = 0;
+    }
     const char* c_env = getenv("B200_MSM_C"); // tuning knob: window width of the cache's MSM plans (0/unset = heuristic)
     const int c_req = c_env ? atoi(c_env) : 0;
     auto plan_for = [&](uint32_t n, bool g2) {
@@ -453,52 +580,97 @@ namespace b200 {
       p.stride = p.factor; // the cache builds its own tables: only the multiples the plan uses
       return p;
     };
-    c->planA = plan_for(c->a_hi - c->a_lo, false);
-    c->planC = c->planA;
-    c->planB2 = c->planA; // same digits/windows as the G1 MSMs: B2 reuses their sort
     c->planH = plan_for(c->h_hi - c->h_lo, false);
     {
       // entries pack the sign in bit 31 of (point index * factor + table column); entry positions are 32-bit
       const uint64_t f = (uint64_t)c->precompute;
-      if ((uint64_t)c->n_vars * f >= (1ull << 31) || (uint64_t)N * f >= (1ull << 31) || c->planA.entries() >= (1ull << 32) ||
-          c->planH.entries() >= (1ull << 32))
+      if ((uint64_t)c->n_vars * f >= (1ull << 31) || (uint64_t)N * f >= (1ull << 31) || c->planH.entries() >= (1ull << 32) ||
+          plan_for(c->n_vars, false).entries() >= (1ull << 32))
         return fail(ICICLE_INVALID_ARGUMENT);
     }
-    if ((err = upload_points<Fq>(c, sec[5], 0, c->a_lo, c->a_hi, c->planA, &c->pA, st)) != ICICLE_SUCCESS) return fail(err);
     {
-      // which signals of the shard have a B point at all? (B1 and B2 are zero together: same v_s(tau))
-      const uint32_t n_sh = c->a_hi - c->a_lo;
-      std::vector<uint32_t> keep;
-      keep.reserve(n_sh);
-      const uint64_t* b1 = reinterpret_cast<const uint64_t*>(sec[6].p) + (size_t)c->a_lo * 8;
-      const uint64_t* b2 = reinterpret_cast<const uint64_t*>(sec[7].p) + (size_t)c->a_lo * 16;
-      for (uint32_t i = 0; i < n_sh; ++i) {
-        uint64_t any = 0;
-        for (int k = 0; k < 8; ++k)
-          any |= b1[(size_t)i * 8 + k];
-        for (int k = 0; k < 16; ++k)
-          any |= b2[(size_t)i * 16 + k];
-        if (any) keep.push_back(i);
+      // which signals of a range have a B point at all? (B1 and B2 are zero together: same v_s(tau))
+      auto keep_list = [&](uint32_t lo, uint32_t hi) {
+        std::vector<uint32_t> keep;
+        keep.reserve(hi - lo);
+        const uint64_t* b1 = reinterpret_cast<const uint64_t*>(sec[6].p) + (size_t)lo * 8;
+        const uint64_t* b2 = reinterpret_cast<const uint64_t*>(sec[7].p) + (size_t)lo * 16;
+        for (uint32_t i = 0; i < hi - lo; ++i) {
+          uint64_t any = 0;
+          for (int k = 0; k < 8; ++k)
+            any |= b1[(size_t)i * 8 + k];
+          for (int k = 0; k < 16; ++k)
+            any |= b2[(size_t)i * 16 + k];
+          if (any) keep.push_back(i);
+        }
+        return keep;
+      };
+      const char* sp_env = getenv("B200_SPARSE_B"); // 0 = never compact, 1 = always (tests), default: >= 1/8 at infinity
+      std::vector<std::vector<uint32_t>> keeps; // per group (empty for dense groups)
+      // the group covering [lo, hi) (compact: with the B columns at infinity dropped), created on first use
+      auto group_for = [&](uint32_t lo, uint32_t hi, bool compact) -> int {
+        for (size_t g = 0; g < c->groups.size(); ++g)
+          if (c->groups[g].lo == lo && c->groups[g].hi == hi && c->groups[g].compact == compact) return (int)g;
+        b200_zkey_cache::WGroup g;
+        g.lo = lo;
+        g.hi = hi;
+        g.compact = compact;
+        keeps.emplace_back();
+        if (compact) {
+          keeps.back() = keep_list(lo, hi);
+          g.n = (uint32_t)keeps.back().size();
+        } else {
+          g.n = hi - lo;
+        }
+        g.plan = plan_for(g.n, false); // B2 shares the digits/windows of the G1 tables: it reuses their sort
+        c->groups.push_back(g);
+        return (int)c->groups.size() - 1;
+      };
+      auto b_is_sparse = [&](uint32_t lo, uint32_t hi) {
+        if (hi <= lo) return false;
+        if (sp_env && sp_env[0] == '0') return false;
+        if (sp_env && sp_env[0] == '1') return true;
+        return (hi - lo - keep_list(lo, hi).size()) * 8 >= (size_t)(hi - lo);
+      };
+      struct SecDesc {
+        int plan_idx, zkey_sec, slot; // slot: 0 = A, 1 = B1, 2 = C, -1 = B2 (G2)
+        uint32_t prefix;
+        bool b;
+      };
+      const SecDesc descs[4] = {{1, 5, 0, 0, false}, {2, 6, 1, 0, true}, {3, 8, 2, c->n_public + 1, false}, {4, 7, -1, 0, true}};
+      for (const SecDesc& d : descs) {
+        const uint32_t lo = c->sec_lo[d.plan_idx], hi = c->sec_hi[d.plan_idx];
+        if (hi <= lo) continue;
+        const bool compact = d.b && b_is_sparse(lo, hi);
+        const int gi = group_for(lo, hi, compact);
+        b200_zkey_cache::WGroup& g = c->groups[gi];
+        if (d.slot == 1) {
+          c->n_b = g.n;
+          c->b_total = hi - lo;
+        }
+        if (compact && !g.idx && g.n) {
+          CK(dev_alloc(&g.idx, (size_t)g.n, c));
+          CK(dev_alloc(&g.d_w, (size_t)g.n, c));
+          CK(cudaMemcpyAsync(g.idx, keeps[gi].data(), (size_t)g.n * 4, cudaMemcpyHostToDevice, st));
+        }
+        if (d.slot >= 0) {
+          G1Affine** dst = &g.g1[g.n_g1];
+          g.g1_slot[g.n_g1++] = d.slot;
+          err = compact ? upload_points_compact<Fq>(c, sec[d.zkey_sec], lo, keeps[gi], g.plan, dst, st)
+                        : upload_points<Fq>(c, sec[d.zkey_sec], d.prefix, lo, hi, g.plan, dst, st);
+        } else {
+          err = compact ? upload_points_compact<Fq2>(c, sec[d.zkey_sec], lo, keeps[gi], g.plan, &g.g2, st)
+                        : upload_points<Fq2>(c, sec[d.zkey_sec], d.prefix, lo, hi, g.plan, &g.g2, st);
+        }
+        if (err != ICICLE_SUCCESS) return fail(err);
       }
-      const char* sp = getenv("B200_SPARSE_B"); // 0 = never compact, 1 = always (tests), default: >= 1/8 at infinity
-      const bool want = sp ? sp[0] == '1' : (n_sh - keep.size()) * 8 >= (size_t)n_sh;
-      if (want && n_sh > 0) {
-        c->b_sparse = true;
-        c->n_b = (uint32_t)keep.size();
-        c->planB2 = plan_for(c->n_b, false);
-        CK(dev_alloc(&c->idxB, keep.size(), c));
-        CK(dev_alloc(&c->d_wb, keep.size(), c));
-        CK(cudaMemcpyAsync(c->idxB, keep.data(), keep.size() * 4, cudaMemcpyHostToDevice, st));
-        if ((err = upload_points_compact<Fq>(c, sec[6], c->a_lo, keep, c->planB2, &c->pB1, st)) != ICICLE_SUCCESS) return fail(err);
-        if ((err = upload_points_compact<Fq2>(c, sec[7], c->a_lo, keep, c->planB2, &c->pB2, st)) != ICICLE_SUCCESS) return fail(err);
-      } else {
-        c->n_b = n_sh;
-        if ((err = upload_points<Fq>(c, sec[6], 0, c->a_lo, c->a_hi, c->planA, &c->pB1, st)) != ICICLE_SUCCESS) return fail(err);
-        if ((err = upload_points<Fq2>(c, sec[7], 0, c->a_lo, c->a_hi, c->planB2, &c->pB2, st)) != ICICLE_SUCCESS) return fail(err);
+      for (auto& g : c->groups) {
+        if (g.n_g1) CK(dev_alloc(&g.d_out, 3, c));
+        CK(cudaEventCreateWithFlags(&g.ev_sort, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&g.ev_done, cudaEventDisableTiming));
       }
+      CK(cudaStreamSynchronize(st)); // the keep lists go out of scope
     }
-    if ((err = upload_points<Fq>(c, sec[8], c->n_public + 1, c->c_lo, c->c_hi, c->planC, &c->pC, st)) != ICICLE_SUCCESS)
-      return fail(err);
     if ((err = upload_points<Fq>(c, sec[9], 0, c->h_lo, c->h_hi, c->planH, &c->pH, st)) != ICICLE_SUCCESS) return fail(err);
     lap("points uploaded, tables queued");
 
@@ -566,11 +738,19 @@ namespace b200 {
     }
 
     // ---- workspace
-    CK(dev_alloc(&c->d_witness, (size_t)c->n_vars, c));
+    c->wit_slice = ((size_t)c->n_vars + world - 1) / world;
+    CK(dev_alloc(&c->d_witness, c->wit_slice * world, c));
     CK(dev_alloc(&c->d_vec, 3 * (size_t)N, c));
     CK(dev_alloc(&c->d_h, (size_t)N, c));
     CK(dev_alloc(&c->d_results, (size_t)4 * 96 + 192, c));
-    CK(dev_alloc(&c->d_scratch_results, (size_t)2 * 96, c));
+    {
+      // result slots no MSM of this rank writes (sections it holds no part of) keep the identity
+      static const G1Projective id1 = {Fq::zero(), Fq::raw_one(), Fq::zero()};
+      static const G2Projective id2 = {Fq2::zero(), {Fq::raw_one(), Fq::zero()}, Fq2::zero()};
+      for (int k = 0; k < 4; ++k)
+        CK(cudaMemcpyAsync(c->d_results + 96 * k, &id1, 96, cudaMemcpyHostToDevice, st));
+      CK(cudaMemcpyAsync(c->d_results + 4 * 96, &id2, 192, cudaMemcpyHostToDevice, st));
+    }
     CK(cudaHostAlloc((void**)&c->h_results, 4 * 96 + 192, cudaHostAllocDefault));
     CK(cudaGetLastError());
     lap("everything queued");
@@ -609,31 +789,31 @@ namespace b200 {
       if (!d || d->max_log < (int)c->power) B200_TRY(ntt_init_domain_host(host_omega((int)c->power), c->s_copy));
     }
     B200_CUDA(cudaEventRecord(c->ev_start, c->s_copy), ICICLE_UNKNOWN_FALLBACK);
-    if (full && c->world > 1 && c->ev_slice && c->a_hi > c->a_lo) {
+    if (full && c->world > 1 && c->ev_slice && c->w_hi > c->w_lo) {
       // sharded rank that also evaluates R1CS rows: its own slice first - the witness MSMs (s_g1, s_g2) start on it
       // while the rest of the witness, which only the quotient chain reads, is still crossing PCIe
       B200_CUDA(
-        cudaMemcpyAsync(c->d_witness + c->a_lo, witness + c->a_lo, (size_t)(c->a_hi - c->a_lo) * 32, cudaMemcpyDefault, c->s_copy),
+        cudaMemcpyAsync(c->d_witness + c->w_lo, witness + c->w_lo, (size_t)(c->w_hi - c->w_lo) * 32, cudaMemcpyDefault, c->s_copy),
         ICICLE_COPY_FAILED);
       B200_CUDA(cudaEventRecord(c->ev_slice, c->s_copy), ICICLE_UNKNOWN_FALLBACK);
-      for (cudaStream_t s : {c->s_g1, c->s_g2})
+      for (cudaStream_t s : {c->s_g1, c->s_g2, c->s_g3})
         B200_CUDA(cudaStreamWaitEvent(s, c->ev_slice, 0), ICICLE_UNKNOWN_FALLBACK);
-      if (c->a_lo > 0)
-        B200_CUDA(cudaMemcpyAsync(c->d_witness, witness, (size_t)c->a_lo * 32, cudaMemcpyDefault, c->s_copy), ICICLE_COPY_FAILED);
-      if (c->a_hi < c->n_vars)
+      if (c->w_lo > 0)
+        B200_CUDA(cudaMemcpyAsync(c->d_witness, witness, (size_t)c->w_lo * 32, cudaMemcpyDefault, c->s_copy), ICICLE_COPY_FAILED);
+      if (c->w_hi < c->n_vars)
         B200_CUDA(
-          cudaMemcpyAsync(c->d_witness + c->a_hi, witness + c->a_hi, (size_t)(c->n_vars - c->a_hi) * 32, cudaMemcpyDefault, c->s_copy),
+          cudaMemcpyAsync(c->d_witness + c->w_hi, witness + c->w_hi, (size_t)(c->n_vars - c->w_hi) * 32, cudaMemcpyDefault, c->s_copy),
           ICICLE_COPY_FAILED);
       B200_CUDA(cudaEventRecord(c->ev_h2d, c->s_copy), ICICLE_UNKNOWN_FALLBACK);
       B200_CUDA(cudaStreamWaitEvent(c->s_q, c->ev_h2d, 0), ICICLE_UNKNOWN_FALLBACK);
       return ICICLE_SUCCESS;
     }
-    const size_t w_lo = full ? 0 : c->a_lo, w_hi = full ? c->n_vars : c->a_hi;
+    const size_t w_lo = full ? 0 : c->w_lo, w_hi = full ? c->n_vars : c->w_hi;
     if (w_hi > w_lo)
       B200_CUDA(
         cudaMemcpyAsync(c->d_witness + w_lo, witness + w_lo, (w_hi - w_lo) * 32, cudaMemcpyDefault, c->s_copy), ICICLE_COPY_FAILED);
     B200_CUDA(cudaEventRecord(c->ev_h2d, c->s_copy), ICICLE_UNKNOWN_FALLBACK);
-    for (cudaStream_t s : {c->s_g1, c->s_g2, c->s_q})
+    for (cudaStream_t s : {c->s_g1, c->s_g2, c->s_g3, c->s_q})
       B200_CUDA(cudaStreamWaitEvent(s, c->ev_h2d, 0), ICICLE_UNKNOWN_FALLBACK);
     return ICICLE_SUCCESS;
   }
@@ -651,110 +831,65 @@ namespace b200 {
   }
 
   // h = a.b - c over this rank's H shard (a, b, c point at the shard's first element), then the H MSM, on s_q
-  static eIcicleError enqueue_h_combine(b200_zkey_cache* c, const Fr* a, const Fr* b, const Fr* cc)
-  {
-    const uint32_t cnt = c->h_hi - c->h_lo;
-    if (cnt) B200_LAUNCH(quotient_combine_kernel, grid_for(cnt, 256, 8), 256, 0, c->s_q, a, b, cc, cnt, c->d_h + c->h_lo);
-    cudaEventRecord(c->ev_ntt, c->s_q);
-    return ICICLE_SUCCESS;
-  }
-  // the H MSM; with a token its accumulation phase waits for *tok and *tok becomes "H accumulated" (see commit_enqueue)
-  static eIcicleError enqueue_h_msm(b200_zkey_cache* c, cudaEvent_t* tok = nullptr)
+  static eIcicleError enqueue_h(b200_zkey_cache* c, const Fr* a, const Fr* b, const Fr* cc)
   {
     const uint32_t cnt = c->h_hi - c->h_lo;
     if (cnt) {
-      if (tok) {
-        tl_msm_hook.wait_before_acc = *tok;
-        tl_msm_hook.record_after_acc = c->ev_tok[3];
-        *tok = c->ev_tok[3];
-      }
+      B200_LAUNCH(quotient_combine_kernel, grid_for(cnt, 256, 8), 256, 0, c->s_q, a, b, cc, cnt, c->d_h + c->h_lo);
+      cudaEventRecord(c->ev_ntt, c->s_q);
       B200_TRY(msm_enqueue<Fq>(c->planH, c->d_h + c->h_lo, false, c->pH, result_slots(c).h, c->s_q));
+    } else {
+      cudaEventRecord(c->ev_ntt, c->s_q);
     }
     cudaEventRecord(c->ev_q, c->s_q);
     return ICICLE_SUCCESS;
   }
-  static eIcicleError enqueue_h(b200_zkey_cache* c, const Fr* a, const Fr* b, const Fr* cc)
-  {
-    B200_TRY(enqueue_h_combine(c, a, b, cc));
-    return enqueue_h_msm(c);
-  }
 
-  // witness-only MSMs (proof_helper.rs:198-206): A, B1, C and B2 take the same scalars over signal-indexed point
-  // tables, so ONE digit decomposition + counting sort feeds one G1 accumulate/reduce over three tables (s_g1) and
-  // one G2 accumulate/reduce (s_g2)
-  // With a token (B200_SCHED) the accumulation phases run one after the other: the first waits for *tok, each next one
-  // for its predecessor, *tok becomes the last one's completion; g1_first picks the order of the G1 and G2 phases.
-  static eIcicleError enqueue_witness_msms(b200_zkey_cache* c, cudaEvent_t* tok = nullptr, bool g1_first = false)
+  // witness-only MSMs (proof_helper.rs:198-206).  G2 parts run on s_g2, the fused G1 parts of successive groups alternate
+  // between s_g1 and s_g3 so that the sort and the latency-bound bucket reduction of one group overlap the accumulation of
+  // another; a group's sort runs on the stream of its G2 part when it has one (the longest consumer), else on its G1 stream
+  // `gate` (optional): the accumulation phases wait for it - a polynomial owner of a sharded proof keeps the multiplier for
+  // its transforms until their slices are on the wire (the other ranks' H MSMs wait for them); the sorts are not gated
+  static eIcicleError enqueue_witness_msms(b200_zkey_cache* c, cudaEvent_t gate = nullptr)
   {
     ResultSlots r = result_slots(c);
-    const Fr* w = c->d_witness;
-    int next_tok = 0;
-    auto chain = [&]() { // arms the hook of the next msm_reduce_enqueue
-      if (!tok) return;
-      tl_msm_hook.wait_before_acc = *tok;
-      tl_msm_hook.record_after_acc = c->ev_tok[next_tok];
-      *tok = c->ev_tok[next_tok++];
-    };
-    if (c->a_hi > c->a_lo && c->b_sparse) {
-      // sparse B: A and C share the signal-indexed sort (s_g1); B1 and B2 share a second, shorter sort over the
-      // gathered witness values of the signals that have a B point (s_g2)
-      MsmSorted sorted_ac, sorted_b;
-      B200_TRY(msm_sort_enqueue(c->planA, w + c->a_lo, false, &sorted_ac, c->s_g1));
-      const G1Affine* ac_tables[2] = {c->pA, c->pC};
-      G1Projective* tmp_ac = (G1Projective*)c->d_scratch_results; // A, C contiguous
-      auto enqueue_ac = [&]() -> eIcicleError {
-        chain();
-        B200_TRY(msm_reduce_enqueue<Fq>(c->planA, sorted_ac, ac_tables, 2, tmp_ac, c->s_g1));
-        cudaMemcpyAsync(r.a, tmp_ac, 96, cudaMemcpyDeviceToDevice, c->s_g1);
-        cudaMemcpyAsync(r.c, tmp_ac + 1, 96, cudaMemcpyDeviceToDevice, c->s_g1);
-        msm_sorted_free(&sorted_ac, c->s_g1);
-        return ICICLE_SUCCESS;
-      };
-      if (!tok || g1_first || c->n_b == 0) B200_TRY(enqueue_ac());
-      if (c->n_b > 0) {
-        B200_LAUNCH(gather_scalars_kernel, grid_for(c->n_b, 256, 8), 256, 0, c->s_g2, w + c->a_lo, c->idxB, c->n_b, c->d_wb);
-        B200_TRY(msm_sort_enqueue(c->planB2, c->d_wb, false, &sorted_b, c->s_g2));
-        const G1Affine* b1_tables[1] = {c->pB1};
-        const G2Affine* b2_tables[1] = {c->pB2};
-        chain();
-        B200_TRY(msm_reduce_enqueue<Fq2>(c->planB2, sorted_b, b2_tables, 1, r.b2, c->s_g2));
-        chain();
-        B200_TRY(msm_reduce_enqueue<Fq>(c->planB2, sorted_b, b1_tables, 1, r.b1, c->s_g2));
-        msm_sorted_free(&sorted_b, c->s_g2);
-        if (tok && !g1_first) B200_TRY(enqueue_ac());
-      } else {
-        // no signal has a B point: both commitments are the identity
-        static const G1Projective id1 = {Fq::zero(), Fq::raw_one(), Fq::zero()};
-        static const G2Projective id2 = {Fq2::zero(), {Fq::raw_one(), Fq::zero()}, Fq2::zero()};
-        cudaMemcpyAsync(r.b1, &id1, 96, cudaMemcpyHostToDevice, c->s_g2);
-        cudaMemcpyAsync(r.b2, &id2, 192, cudaMemcpyHostToDevice, c->s_g2);
+    G1Projective* const slot[3] = {r.a, r.b1, r.c};
+    int g1_turn = 0;
+    for (const auto& g : c->groups) {
+      if (!g.n) continue;
+      cudaStream_t sg1 = g.n_g1 ? ((g1_turn++ & 1) ? c->s_g3 : c->s_g1) : nullptr;
+      cudaStream_t ss = g.g2 ? c->s_g2 : sg1;
+      const Fr* sc = c->d_witness + g.lo;
+      if (g.compact) {
+        B200_LAUNCH(gather_scalars_kernel, grid_for(g.n, 256, 8), 256, 0, ss, sc, g.idx, g.n, g.d_w);
+        sc = g.d_w;
       }
-      cudaEventRecord(c->ev_g2, c->s_g2);
-    } else if (c->a_hi > c->a_lo) {
       MsmSorted sorted;
-      B200_TRY(msm_sort_enqueue(c->planA, w + c->a_lo, false, &sorted, c->s_g1));
-      cudaEventRecord(c->ev_b1, c->s_g1); // sort done
-      cudaStreamWaitEvent(c->s_g2, c->ev_b1, 0);
-      const G1Affine* g1_tables[3] = {c->pA, c->pB1, c->pC};
-      const G2Affine* g2_tables[1] = {c->pB2};
-      if (tok && !g1_first) {
-        chain();
-        B200_TRY(msm_reduce_enqueue<Fq2>(c->planB2, sorted, g2_tables, 1, r.b2, c->s_g2));
-        chain();
-        B200_TRY(msm_reduce_enqueue<Fq>(c->planA, sorted, g1_tables, 3, r.a, c->s_g1));
-      } else {
-        chain();
-        B200_TRY(msm_reduce_enqueue<Fq>(c->planA, sorted, g1_tables, 3, r.a, c->s_g1));
-        chain();
-        B200_TRY(msm_reduce_enqueue<Fq2>(c->planB2, sorted, g2_tables, 1, r.b2, c->s_g2));
+      B200_TRY(msm_sort_enqueue(g.plan, sc, false, &sorted, ss));
+      if (g.g2) {
+        if (g.n_g1) {
+          cudaEventRecord(g.ev_sort, ss);
+          cudaStreamWaitEvent(sg1, g.ev_sort, 0);
+        }
+        const G2Affine* g2_tables[1] = {g.g2};
+        B200_TRY(msm_reduce_enqueue<Fq2>(g.plan, sorted, g2_tables, 1, r.b2, c->s_g2, gate));
       }
-      cudaEventRecord(c->ev_g2, c->s_g2);
-      cudaStreamWaitEvent(c->s_g1, c->ev_g2, 0); // the sort's scratch is released after both consumers
-      msm_sorted_free(&sorted, c->s_g1);
-    } else {
-      cudaEventRecord(c->ev_g2, c->s_g2);
+      if (g.n_g1) {
+        const G1Affine* g1_tables[3] = {g.g1[0], g.g1[g.n_g1 > 1 ? 1 : 0], g.g1[g.n_g1 > 2 ? 2 : 0]};
+        B200_TRY(msm_reduce_enqueue<Fq>(g.plan, sorted, g1_tables, g.n_g1, g.d_out, sg1, gate));
+        for (int k = 0; k < g.n_g1; ++k)
+          cudaMemcpyAsync(slot[g.g1_slot[k]], g.d_out + k, 96, cudaMemcpyDeviceToDevice, sg1);
+        if (g.g2) { // the sort's scratch is released after both consumers
+          cudaEventRecord(g.ev_done, sg1);
+          cudaStreamWaitEvent(ss, g.ev_done, 0);
+        }
+      }
+      msm_sorted_free(&sorted, ss);
     }
+    cudaEventRecord(c->ev_free, c->s_g3); // s_g3 joins s_g1
+    cudaStreamWaitEvent(c->s_g1, c->ev_free, 0);
     cudaEventRecord(c->ev_g1, c->s_g1);
+    cudaEventRecord(c->ev_g2, c->s_g2);
     return ICICLE_SUCCESS;
   }
 
@@ -775,20 +910,8 @@ namespace b200 {
     B200_TRY(enqueue_upload(c, witness, n_witness));
     const uint32_t N = c->domain_size;
     B200_TRY(enqueue_quotient_polys(c, 0, 3, c->d_vec)); // quotient chain + H on the (higher-priority) s_q
-    if (c->sched == 0) {
-      B200_TRY(enqueue_h(c, c->d_vec + c->h_lo, c->d_vec + N + c->h_lo, c->d_vec + 2 * (size_t)N + c->h_lo));
-      B200_TRY(enqueue_witness_msms(c));
-      return enqueue_join(c);
-    }
-    // B200_SCHED: every phase below saturates the integer multiply pipe on its own, so running them concurrently buys
-    // nothing and makes their latency-bound reduction tails end together.  One after the other instead - the transform
-    // chain first, then (1) G2, G1, H  (2) G1, G2, H  (3) H, G2, G1  (4) H, G1, G2 - while the sorts and the bucket
-    // reductions of the neighbours overlap the running accumulation.
-    B200_TRY(enqueue_h_combine(c, c->d_vec + c->h_lo, c->d_vec + N + c->h_lo, c->d_vec + 2 * (size_t)N + c->h_lo));
-    cudaEvent_t tok = c->ev_ntt;
-    if (c->sched >= 3) B200_TRY(enqueue_h_msm(c, &tok));
-    B200_TRY(enqueue_witness_msms(c, &tok, c->sched == 2 || c->sched == 4));
-    if (c->sched < 3) B200_TRY(enqueue_h_msm(c, &tok));
+    B200_TRY(enqueue_h(c, c->d_vec + c->h_lo, c->d_vec + N + c->h_lo, c->d_vec + 2 * (size_t)N + c->h_lo));
+    B200_TRY(enqueue_witness_msms(c));
     return enqueue_join(c);
   }
 
@@ -798,17 +921,8 @@ namespace b200 {
     B200_CUDA(cudaStreamSynchronize(c->s_copy), ICICLE_SYNCHRONIZATION_FAILED);
     B200_CUDA(cudaGetLastError(), ICICLE_UNKNOWN_FALLBACK);
 
-    // empty shards contribute the identity
-    G1Projective id1 = {Fq::zero(), Fq::raw_one(), Fq::zero()};
-    G2Projective id2 = {Fq2::zero(), {Fq::raw_one(), Fq::zero()}, Fq2::zero()};
+    // sections this rank holds no part of contribute the identity (written into the result slots at cache build)
     memcpy(out, c->h_results, 4 * 96 + 192);
-    if (c->a_hi == c->a_lo) {
-      memcpy(&out->a, &id1, 96);
-      memcpy(&out->b1, &id1, 96);
-      memcpy(&out->c, &id1, 96);
-      memcpy(&out->b2, &id2, 192);
-    }
-    if (c->h_hi == c->h_lo) memcpy(&out->h, &id1, 96);
     if (tm) {
       cudaEventSynchronize(c->ev_q);
       cudaEventSynchronize(c->ev_g1);
@@ -903,8 +1017,7 @@ namespace b200 {
     // pi_c = C + H + s*pi_a + r*pi_b1 - (r*s)*delta1
     G1XYZZ pi_c = C;
     pi_c.add(H);
-    pi_c.add(host_scalar_mul(pi_a, s));
-    pi_c.add(host_scalar_mul(pi_b1, r));
+    pi_c.add(host_double_scalar_mul(pi_a, s, pi_b1, r));
     pi_c.add(bt.rs_d1.neg());
 
     G1Affine a = affine_from_mont(pi_a.to_affine());
@@ -1103,7 +1216,36 @@ eIcicleError b200_zkey_cache_b_points(const b200_zkey_cache* c, uint32_t* kept, 
 {
   if (!c || !kept || !total) return ICICLE_INVALID_POINTER;
   *kept = c->n_b;
-  *total = c->a_hi - c->a_lo;
+  *total = c->b_total;
+  return ICICLE_SUCCESS;
+}
+
+// The cut of the five base-point sections (0 = H, 1 = A, 2 = B1, 3 = C, 4 = B2) a rank of `world` holds.
+// mode: 0 = uniform (every section cut `world` ways; `skew` as in b200_shard_range), 1 = line (sections laid end to end by
+// cost and cut into equal-cost pieces), -1 = the library default (B200_SHARD_PLAN; line for world > 1).
+eIcicleError b200_shard_plan(uint32_t n_vars, uint32_t domain_size, int rank, int world, int mode, double skew, uint32_t* lo5, uint32_t* hi5)
+{
+  if (!lo5 || !hi5) return ICICLE_INVALID_POINTER;
+  if (world < 1 || rank < 0 || rank >= world || mode < -1 || mode > 1) return ICICLE_INVALID_ARGUMENT;
+  const ShardPlan sp = shard_plan(n_vars, domain_size, rank, world, mode < 0 ? plan_mode_default(world) : mode, skew);
+  for (int k = 0; k < 5; ++k) {
+    lo5[k] = sp.lo[k];
+    hi5[k] = sp.hi[k];
+  }
+  return ICICLE_SUCCESS;
+}
+
+// the mode b200_zkey_cache_create_sharded cuts with for this world size (environment included): 0 uniform, 1 line
+int b200_shard_plan_mode(int world) { return plan_mode_default(world); }
+
+// the ranges this cache was built with
+eIcicleError b200_zkey_cache_ranges(const b200_zkey_cache* c, uint32_t* lo5, uint32_t* hi5)
+{
+  if (!c || !lo5 || !hi5) return ICICLE_INVALID_POINTER;
+  for (int k = 0; k < 5; ++k) {
+    lo5[k] = c->sec_lo[k];
+    hi5[k] = c->sec_hi[k];
+  }
   return ICICLE_SUCCESS;
 }
 
@@ -1178,20 +1320,45 @@ eIcicleError b200_groth16_prove_sharded(
     B200_CUDA(dev_alloc(&c->d_all_parts, (size_t)world * sizeof(b200_groth16_partials), c), ICICLE_ALLOCATION_FAILED);
     B200_CUDA(cudaMallocHost((void**)&c->h_all_parts, (size_t)world * sizeof(b200_groth16_partials)), ICICLE_ALLOCATION_FAILED);
     B200_CUDA(cudaEventCreateWithFlags(&c->ev_slice, cudaEventDisableTiming), ICICLE_UNKNOWN_FALLBACK);
-    // result slots no MSM of this rank ever writes (empty shards) hold the identity
-    static const G1Projective id1 = {Fq::zero(), Fq::raw_one(), Fq::zero()};
-    static const G2Projective id2 = {Fq2::zero(), {Fq::raw_one(), Fq::zero()}, Fq2::zero()};
-    ResultSlots rs = result_slots(c);
-    for (G1Projective* p : {rs.a, rs.b1, rs.c, rs.h})
-      B200_CUDA(cudaMemcpy(p, &id1, 96, cudaMemcpyHostToDevice), ICICLE_COPY_FAILED);
-    B200_CUDA(cudaMemcpy(rs.b2, &id2, 192, cudaMemcpyHostToDevice), ICICLE_COPY_FAILED);
+    B200_CUDA(cudaEventCreateWithFlags(&c->ev_xch, cudaEventDisableTiming), ICICLE_UNKNOWN_FALLBACK);
   }
-  eIcicleError e = enqueue_upload(c, witness, n_witness, count > 0);
+  // A HOST witness crosses PCIe once per box, not once per GPU: every rank uploads 1/world of it and one ncclAllGather
+  // over NVLink completes it everywhere (8 GPUs pulling 102 MB each through the host cost 6.7 ms at 3200k; this is 0.6 ms).
+  // A DEVICE witness is copied as before.
+  eIcicleError e = ICICLE_SUCCESS;
+  bool wit_on_host = true;
+  {
+    cudaPointerAttributes pa;
+    if (cudaPointerGetAttributes(&pa, witness) == cudaSuccess)
+      wit_on_host = !(pa.type == cudaMemoryTypeDevice || pa.type == cudaMemoryTypeManaged);
+    (void)cudaGetLastError();
+  }
+  if (world > 1 && wit_on_host && c->wit_slice > 0) { // (every rank must pass the same kind of memory: this is a collective)
+    if (n_witness != c->n_vars) return ICICLE_INVALID_ARGUMENT;
+    const size_t sl = c->wit_slice, lo = std::min((size_t)rank * sl, (size_t)c->n_vars), hi = std::min(lo + sl, (size_t)c->n_vars);
+    {
+      const NttDomain* d = ntt_domain();
+      if (d && d->max_log < (int)c->power) bn254_ntt_release_domain();
+      if (!d || d->max_log < (int)c->power) B200_TRY(ntt_init_domain_host(host_omega((int)c->power), c->s_copy));
+    }
+    cudaEventRecord(c->ev_start, c->s_copy);
+    if (hi > lo && cudaMemcpyAsync(c->d_witness + lo, witness + lo, (hi - lo) * 32, cudaMemcpyDefault, c->s_copy) != cudaSuccess)
+      e = ICICLE_COPY_FAILED;
+    if (e == ICICLE_SUCCESS &&
+        nccl().AllGather(c->d_witness + (size_t)rank * sl, c->d_witness, sl * 32, ncclUint8, comm->comm, c->s_copy) != ncclSuccess)
+      e = (eIcicleError)ICICLE_UNKNOWN_FALLBACK;
+    cudaEventRecord(c->ev_h2d, c->s_copy);
+    for (cudaStream_t st : {c->s_g1, c->s_g2, c->s_g3, c->s_q})
+      cudaStreamWaitEvent(st, c->ev_h2d, 0);
+  } else {
+    e = enqueue_upload(c, witness, n_witness, count > 0);
+  }
   if (e == ICICLE_SUCCESS && count > 0) e = enqueue_quotient_polys(c, first, count, c->d_vec + (size_t)first * N);
   if (e == ICICLE_SUCCESS && count == 0) cudaEventRecord(c->ev_r1cs, c->s_q);
-  if (e == ICICLE_SUCCESS) e = enqueue_witness_msms(c);
+  // ranks that own no polynomial start their witness MSMs at once; the owners queue theirs behind the exchange (below)
+  if (e == ICICLE_SUCCESS && count == 0) e = enqueue_witness_msms(c);
   if (e == ICICLE_SUCCESS) {
-    // the exchange: polynomial j's owner holds all of it; rank q needs [N q / world, N (q+1) / world)
+    // the exchange: polynomial j's owner holds all of it; rank q needs the range of its H piece (shard_plan)
     ncclResult_t nr = nccl().GroupStart();
     for (int j = 0; j < 3 && nr == ncclSuccess; ++j) {
       const int owner = owner_of(j);
@@ -1199,8 +1366,8 @@ eIcicleError b200_groth16_prove_sharded(
       if (owner == rank) {
         const Fr* poly = c->d_vec + (size_t)j * N;
         for (int q = 0; q < world && nr == ncclSuccess; ++q) {
-          uint32_t lo, hi;
-          shard(N, q, world, &lo, &hi);
+          const ShardPlan spq = shard_plan(c->n_vars, N, q, world, c->plan_mode, c->plan_skew);
+          const uint32_t lo = spq.lo[0], hi = spq.hi[0];
           if (hi == lo) continue;
           if (q == rank)
             cudaMemcpyAsync(mine, poly + lo, (size_t)(hi - lo) * 32, cudaMemcpyDeviceToDevice, c->s_q);
@@ -1216,6 +1383,10 @@ eIcicleError b200_groth16_prove_sharded(
       fprintf(stderr, "[icicle_b200] quotient exchange: %s\n", nccl().GetErrorString(nr != ncclSuccess ? nr : ge));
       e = (eIcicleError)ICICLE_UNKNOWN_FALLBACK;
     }
+  }
+  if (e == ICICLE_SUCCESS && count > 0) {
+    cudaEventRecord(c->ev_xch, c->s_q);
+    e = enqueue_witness_msms(c, c->ev_xch);
   }
   // d_vec order: 0 = B.w', 1 = A.w', 2 = product'; enqueue_h takes (a, b, c) = (A', B', product')
   if (e == ICICLE_SUCCESS) e = enqueue_h(c, c->qx_slices + (size_t)cnt, c->qx_slices, c->qx_slices + 2 * (size_t)cnt);

@@ -74,10 +74,11 @@ namespace b200 {
 
   // Accumulate + reduce `nsel` (<= 4) MSMs that share `sorted` (same scalars, same plan) over different base-point
   // arrays; out_std[k] receives MSM k in the reference's boundary layout.
+  // `gate` (optional): the bucket-accumulation phase waits for this event (the scratch allocation before it does not)
   template <class F>
   eIcicleError msm_reduce_enqueue(
     const MsmPlan& plan, const MsmSorted& sorted, const Affine<F>* const* bases_mont, int nsel, Projective<F>* out_std,
-    cudaStream_t st);
+    cudaStream_t st, cudaEvent_t gate = nullptr);
 
   // Enqueue one MSM on `st`.  All pointers are DEVICE pointers; `bases_mont` holds n*factor affine
   // points in Montgomery form ([i*f + j] = 2^(shift*j) P_i); `out_std` receives the result in the
@@ -102,13 +103,6 @@ namespace b200 {
     int g2, nsel, n, windows, c, factor, nbuckets, batched; // batched: rounds of batched-affine accumulation (0 = XYZZ)
     float ms;
   };
-  // Phase hook for callers that schedule several MSMs on different streams (groth16.cu): the NEXT msm_reduce_enqueue issued
-  // by this host thread waits for `wait_before_acc` right before its bucket-accumulation phase (the sort phases stay free
-  // to overlap) and records `record_after_acc` right after it (before the latency-bound bucket reduction).  Consumed on use.
-  struct MsmPhaseHook {
-    cudaEvent_t wait_before_acc = nullptr, record_after_acc = nullptr;
-  };
-  extern thread_local MsmPhaseHook tl_msm_hook;
   extern int g_profile_mode;
   void msm_profile_begin(cudaStream_t st);
   void msm_profile_end(cudaStream_t st, const MsmPlan& plan, int g2, int nsel, int batched);

@@ -10,7 +10,6 @@ namespace b200 {
 
   unsigned long long g_launches = 0;
   int g_profile_mode = 0;
-  thread_local MsmPhaseHook tl_msm_hook;
   static cudaEvent_t g_profile_events[2] = {nullptr, nullptr};
   static std::vector<MsmProfileRec> g_profile_recs;
   static std::mutex g_profile_mu;
@@ -97,7 +96,7 @@ namespace b200 {
   }
 
   template eIcicleError msm_enqueue<Fq>(const MsmPlan&, const Fr*, bool, const Affine<Fq>*, Projective<Fq>*, cudaStream_t);
-  template eIcicleError msm_reduce_enqueue<Fq>(const MsmPlan&, const MsmSorted&, const Affine<Fq>* const*, int, Projective<Fq>*, cudaStream_t);
+  template eIcicleError msm_reduce_enqueue<Fq>(const MsmPlan&, const MsmSorted&, const Affine<Fq>* const*, int, Projective<Fq>*, cudaStream_t, cudaEvent_t);
   template eIcicleError precompute_enqueue<Fq>(const Affine<Fq>*, bool, int, int, int, Affine<Fq>*, bool, cudaStream_t);
 
 } // namespace b200

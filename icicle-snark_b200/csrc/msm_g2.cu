@@ -4,7 +4,7 @@
 
 namespace b200 {
   template eIcicleError msm_enqueue<Fq2>(const MsmPlan&, const Fr*, bool, const Affine<Fq2>*, Projective<Fq2>*, cudaStream_t);
-  template eIcicleError msm_reduce_enqueue<Fq2>(const MsmPlan&, const MsmSorted&, const Affine<Fq2>* const*, int, Projective<Fq2>*, cudaStream_t);
+  template eIcicleError msm_reduce_enqueue<Fq2>(const MsmPlan&, const MsmSorted&, const Affine<Fq2>* const*, int, Projective<Fq2>*, cudaStream_t, cudaEvent_t);
   template eIcicleError precompute_enqueue<Fq2>(const Affine<Fq2>*, bool, int, int, int, Affine<Fq2>*, bool, cudaStream_t);
 } // namespace b200
 

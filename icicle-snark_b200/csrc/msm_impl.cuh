@@ -361,10 +361,8 @@ namespace b200 {
   template <class F>
   eIcicleError msm_reduce_enqueue(
     const MsmPlan& plan, const MsmSorted& sorted, const Affine<F>* const* bases_mont, int nsel, Projective<F>* out_std,
-    cudaStream_t st)
+    cudaStream_t st, cudaEvent_t gate)
   {
-    const MsmPhaseHook hook = tl_msm_hook; // consumed whatever happens below
-    tl_msm_hook = MsmPhaseHook();
     if (nsel < 1 || nsel > MSM_MAX_SEL) return ICICLE_INVALID_ARGUMENT;
     MsmDev pl = msm_dev_plan(plan);
     const int nb = plan.nbuckets;
@@ -401,7 +399,7 @@ namespace b200 {
     const unsigned ysel = (unsigned)nsel;
 
     const int ba_rounds = msm_batch_affine_rounds(plan, sizeof(F) > sizeof(Fq));
-    if (hook.wait_before_acc) cudaStreamWaitEvent(st, hook.wait_before_acc, 0);
+    if (gate) cudaStreamWaitEvent(st, gate, 0);
     msm_profile_begin(st);
     if (ba_rounds) {
       // long buckets: pairwise tree of batched affine additions (msm_batch_affine.cuh), 6-7 products per add
@@ -422,7 +420,6 @@ namespace b200 {
         sorted.item_off, partials, buckets, (uint32_t)nb, (uint32_t)max_items);
     }
     msm_profile_end(st, plan, sizeof(F) > sizeof(Fq) ? 1 : 0, nsel, ba_rounds);
-    if (hook.record_after_acc) cudaEventRecord(hook.record_after_acc, st);
     B200_LAUNCH(
       msm_reduce_chunks_kernel<F>, grid_for((size_t)nsets * chunks_per_set, 128, 16), 128, 0, st, pl, nsel, sorted.offsets, buckets,
       chunk_sums, chunk_runs, sum_stride);

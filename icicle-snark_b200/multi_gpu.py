@@ -18,6 +18,17 @@ def shard_range(n: int, rank: int, world: int):
     return n * rank // world, n * (rank + 1) // world
 
 
+def shard_plan(lib, n_vars: int, domain_size: int, rank: int, world: int, mode: int = -1, skew: float = 0.0):
+    """[(lo, hi)] x 5 for the sections (H, A, B1, C, B2) that `rank` holds - the library's own planner
+    (b200_shard_plan; mode -1 = its default: the cost-weighted line cut for world > 1, see include/icicle_b200.h)."""
+    lo, hi = (C.c_uint32 * 5)(), (C.c_uint32 * 5)()
+    rc = lib.dll.b200_shard_plan(C.c_uint32(n_vars), C.c_uint32(domain_size), C.c_int(rank), C.c_int(world), C.c_int(mode),
+                                 C.c_double(skew), lo, hi)
+    if rc != 0:
+        raise ValueError(f"b200_shard_plan failed: {rc}")
+    return [(int(lo[k]), int(hi[k])) for k in range(5)]
+
+
 def partials_to_tensor(parts: Groth16Partials, device):
     import torch
     return torch.frombuffer(bytearray(bytes(parts)), dtype=torch.int32).to(device)
@@ -62,10 +73,12 @@ class QuotientExchange:
         self.N = cache.domain_size
         self.first, self.count = owned_polys(self.rank, self.world)
         self.mine = torch.empty((max(self.count, 1), self.N, 8), dtype=torch.int32, device=device)
-        self.ranges = [shard_range(self.N, r, self.world) for r in range(self.world)]
+        import os
+        skew = float(os.environ.get("B200_SHARD_SKEW", "0") or 0)
+        self.ranges = [shard_plan(cache.lib, cache.n_vars, self.N, r, self.world, -1, skew)[0] for r in range(self.world)]
         lo, hi = self.ranges[self.rank]
         assert (lo, hi) == cache.h_range()
-        self.slices = torch.empty((3, hi - lo, 8), dtype=torch.int32, device=device)
+        self.slices = torch.empty((3, max(hi - lo, 1), 8), dtype=torch.int32, device=device)
 
     def commit(self, witness, n_witness=None):
         self.cache.commit_begin(witness, self.first, self.count, self.mine.data_ptr(), n_witness=n_witness)
@@ -75,7 +88,22 @@ class QuotientExchange:
             if self.rank == owner:
                 src = self.mine[j - self.first]
                 sl = [src[lo:hi] for lo, hi in self.ranges]
-            self.dist.scatter(self.slices[j], scatter_list=sl, src=owner)
+            # (ranks differ in slice length under the line plan: point-to-point instead of scatter)
+            reqs = []
+            if self.rank == owner:
+                for q, (lo, hi) in enumerate(self.ranges):
+                    if hi == lo:
+                        continue
+                    if q == self.rank:
+                        self.slices[j][:hi - lo].copy_(sl[q])
+                    else:
+                        reqs.append(self.dist.isend(sl[q].contiguous(), dst=q))
+            else:
+                lo, hi = self.ranges[self.rank]
+                if hi > lo:
+                    reqs.append(self.dist.irecv(self.slices[j][:hi - lo], src=owner))
+            for rq in reqs:
+                rq.wait()
         self.torch.cuda.current_stream().synchronize()
         # d_vec order: 0 = B.w', 1 = A.w', 2 = product'; commit_end takes (a, b, c) = (A', B', product')
         return self.cache.commit_end(self.slices[1].data_ptr(), self.slices[0].data_ptr(), self.slices[2].data_ptr())

@@ -87,6 +87,12 @@ class ZKeyCache:
         check(self.lib.dll.b200_zkey_cache_h_range(self.handle, C.byref(lo), C.byref(hi)))
         return lo.value, hi.value
 
+    def ranges(self):
+        """[(lo, hi)] x 5: the part of the sections (H, A, B1, C, B2) this cache holds (b200_zkey_cache_ranges)."""
+        lo, hi = (C.c_uint32 * 5)(), (C.c_uint32 * 5)()
+        check(self.lib.dll.b200_zkey_cache_ranges(self.handle, lo, hi))
+        return [(int(lo[k]), int(hi[k])) for k in range(5)]
+
     def b_points(self):
         kept, total = C.c_uint32(), C.c_uint32()
         check(self.lib.dll.b200_zkey_cache_b_points(self.handle, C.byref(kept), C.byref(total)))

@@ -315,13 +315,28 @@ eIcicleError b200_zkey_cache_b_points(const b200_zkey_cache* cache, uint32_t* ke
 eIcicleError b200_groth16_finish(const b200_zkey_cache* cache, const b200_groth16_partials* parts, int n_parts,
                                  const bn254_scalar_t* r, const bn254_scalar_t* s, b200_groth16_proof* proof);
 
+/* The cut of the five base-point sections (0 = H, 1 = A, 2 = B1, 3 = C, 4 = B2) that rank `rank` of `world` holds
+ * (SURVEY 8e).  mode 0 "uniform": every section cut `world` ways (H equally, the signal-indexed ones with `skew`, see
+ * b200_shard_range); mode 1 "line": the sections laid end to end, weighted by cost per point, the quotient-polynomial
+ * transforms charged to their owners, cut into `world` pieces of equal cost - a rank holds one or two large pieces
+ * (whole tables where possible) and keeps the wide Pippenger windows of the single-GPU plan; mode -1: the library
+ * default (environment B200_SHARD_PLAN = uniform | line; unset: line for 2 and for >= 6 ranks, uniform otherwise - the
+ * measured optimum at 3200k constraints).  b200_zkey_cache_create_sharded cuts
+ * with the default mode; b200_zkey_cache_ranges reports what a cache holds. */
+eIcicleError b200_shard_plan(uint32_t n_vars, uint32_t domain_size, int rank, int world, int mode, double skew,
+                             uint32_t* lo5, uint32_t* hi5);
+eIcicleError b200_zkey_cache_ranges(const b200_zkey_cache* cache, uint32_t* lo5, uint32_t* hi5);
+int b200_shard_plan_mode(int world); /* the default mode for this world size: 0 uniform, 1 line */
+
 /* ---- multi-GPU data plane inside the library (one process per GPU; NCCL resolved at run time, csrc/comm.cuh) --------
  * The reference has no multi-GPU path (device 0 is hard-coded, src/lib.rs:29); these entry points are what a host in
  * any language binds to shard one proof or one MSM over the GPUs of a box.
  *   b200_comm_unique_id   rank 0 draws the 128-byte rendezvous token; the host hands it to the other ranks
  *   b200_comm_create      collective: joins the communicator on the calling thread's active device
- *   b200_groth16_prove_sharded  one proof over comm->world GPUs: every rank passes the same witness (host or device
- *                         memory) and a cache built with b200_zkey_cache_create_sharded(rank, world); quotient-polynomial
+ *   b200_groth16_prove_sharded  one proof over comm->world GPUs: every rank passes the same witness (all ranks host
+ *                         memory or all ranks device memory: a host witness is uploaded 1/world per rank and completed by
+ *                         one ncclAllGather over NVLink) and a cache built with b200_zkey_cache_create_sharded(rank, world);
+ *                         polynomial owners hold their witness-MSM accumulations until their slices are sent; quotient-polynomial
  *                         slices travel by one grouped ncclSend/ncclRecv on the library's streams, the partial sums by
  *                         one 576-byte ncclAllGather; rank 0 folds, blinds and writes `proof` (others may pass NULL)
  *   b200_msm_sharded      every rank holds a contiguous slice of scalars and points (same config semantics as

@@ -45,6 +45,11 @@ def _has_gpu():
 
 
 HAS_GPU = _has_gpu()
+if HAS_GPU:
+    # torch before any other CUDA library is loaded into the process: the reference's CUDA backend (second oracle,
+    # oracle/_ref_cuda) exports its runtime globally, and importing torch after it has been loaded segfaults inside
+    # torch's own initialisation.  Whole-suite runs import torch at collection anyway; this makes any -k selection safe.
+    import torch  # noqa: F401
 
 
 def pytest_collection_modifyitems(config, items):

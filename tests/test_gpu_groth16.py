@@ -107,12 +107,42 @@ def test_sharded_partials_fold_to_the_same_proof(gpu):
             c.close()
 
 
+@pytest.mark.parametrize("plan", ["line", "uniform"])
+@pytest.mark.parametrize("world", [2, 3, 4, 8])
+@pytest.mark.parametrize("sparse_b", ["0", "1"])
+def test_shard_plans_fold_to_the_golden_proof(gpu, monkeypatch, plan, world, sparse_b):
+    """Every cut of the five base-point sections over `world` ranks (b200_shard_plan: the cost-weighted line cut - ranks
+    hold different parts of different sections, some none of a section - and the uniform cut), dense and compacted B
+    tables: the partial sums fold to the committed golden proof byte for byte, and the ranges partition every section."""
+    monkeypatch.setenv("B200_SHARD_PLAN", plan)
+    monkeypatch.setenv("B200_SPARSE_B", sparse_b)
+    for n in (6, 100):
+        zkey, wtns, vk, gold11, goldrs, _ = load(n)
+        w = wtns_words(wtns)
+        caches = [pkg.ZKeyCache(gpu, zkey, precompute=(1, 16)[r & 1], rank=r, world=world) for r in range(world)]
+        try:
+            rng_all = [c.ranges() for c in caches]
+            sizes = (caches[0].domain_size,) + (caches[0].n_vars,) * 4
+            for k in range(5):
+                assert rng_all[0][k][0] == 0 and rng_all[-1][k][1] == sizes[k]
+                assert all(rng_all[r][k][1] == rng_all[r + 1][k][0] for r in range(world - 1))
+            assert rng_all == [pkg.multi_gpu.shard_plan(gpu, caches[0].n_vars, caches[0].domain_size, r, world) for r in range(world)]
+            parts = [c.commit_partials(w)[0] for c in caches]
+            assert pkg.proof_json(caches[0].finish(parts, FIXED_R, FIXED_S)) == goldrs
+            parts = [c.commit_partials(w)[0] for c in caches]  # second proof on the same caches
+            assert pkg.proof_json(caches[0].finish(parts, 1, 1)) == gold11
+        finally:
+            for c in caches:
+                c.close()
+
+
 def test_skewed_shards_fold_to_the_same_proof(gpu, monkeypatch):
     # B200_SHARD_SKEW (bench.py sets it when the quotient chain is split): polynomial owners hold smaller witness shards;
     # any partition must fold to the same proof
     zkey, wtns, vk, gold11, goldrs, _ = load(100)
     w = wtns_words(wtns)
     monkeypatch.setenv("B200_SHARD_SKEW", "0.1")
+    monkeypatch.setenv("B200_SHARD_PLAN", "uniform")
     caches = [pkg.ZKeyCache(gpu, zkey, precompute=p, rank=r, world=4) for r, p in zip(range(4), (1, 16, 1, 16))]
     try:
         sizes = [c.b_points()[1] for c in caches]

@@ -123,3 +123,44 @@ def test_skewed_witness_shards_partition_and_balance(lib):
     lo, hi = C.c_uint32(), C.c_uint32()
     assert lib.dll.b200_shard_range(C.c_uint32(10), 3, 3, C.c_double(0.0), C.byref(lo), C.byref(hi)) == 11
     assert lib.dll.b200_shard_range(C.c_uint32(10), 0, 1, C.c_double(0.0), None, C.byref(hi)) == 3
+
+
+def test_line_plan_partitions_and_balances(lib, monkeypatch):
+    """b200_shard_plan mode 1: the five sections (H, A, B1, C, B2) laid end to end by cost and cut into `world` pieces.
+    Every section is partitioned exactly; the weighted load (points x cost + the owners' polynomial transforms) is equal
+    across ranks up to the snapping of cuts to section edges; a rank holds at most two partial sections."""
+    import icicle_snark_b200 as pkg
+    for name in ("B200_SHARD_PLAN", "B200_PLAN_W2", "B200_PLAN_WH", "B200_PLAN_WNTT"):
+        monkeypatch.delenv(name, raising=False)
+    w2, wh, wntt = 3.0, 1.1, 0.24
+    for n_vars, N in ((8, 8), (102, 128), (3_200_002, 1 << 22), (100_002, 1 << 17)):
+        sizes = (N, n_vars, n_vars, n_vars, n_vars)
+        for world in (1, 2, 3, 4, 5, 8, 16):
+            plans = [pkg.multi_gpu.shard_plan(lib, n_vars, N, r, world, 1) for r in range(world)]
+            for k in range(5):
+                assert plans[0][k][0] == 0 and plans[-1][k][1] == sizes[k]
+                assert all(plans[r][k][1] == plans[r + 1][k][0] and plans[r][k][0] <= plans[r][k][1] for r in range(world - 1))
+            if world == 1 or n_vars < 1000:
+                continue
+            wt = (wh, 1, 1, 1, w2)
+            load = []
+            for r in range(world):
+                owned = pkg.multi_gpu.owned_polys(r, world)[1]
+                load.append(sum((hi - lo) * wt[k] for k, (lo, hi) in enumerate(plans[r])) + owned * wntt * N)
+                partial = sum(1 for k, (lo, hi) in enumerate(plans[r]) if hi > lo and (lo > 0 or hi < sizes[k]))
+                assert partial <= 2, (world, r, plans[r])
+            total = sum(load)
+            # snapping moves a cut by at most 4 % of a section
+            assert max(load) - min(load) <= 0.09 * max(sizes) * w2 + 2 * w2, (world, load)
+            assert abs(total - (wh * N + (3 + w2) * n_vars + 3 * wntt * N)) < 1e-3 * total
+    # mode 0 is the uniform cut of b200_shard_range; -1 follows the environment
+    assert pkg.multi_gpu.shard_plan(lib, 1000, 1024, 1, 4, 0) == [(256, 512)] + [(250, 500)] * 4
+    monkeypatch.setenv("B200_SHARD_PLAN", "uniform")
+    assert pkg.multi_gpu.shard_plan(lib, 1000, 1024, 1, 4, -1) == pkg.multi_gpu.shard_plan(lib, 1000, 1024, 1, 4, 0)
+    monkeypatch.setenv("B200_SHARD_PLAN", "line")
+    assert pkg.multi_gpu.shard_plan(lib, 1000, 1024, 1, 4, -1) == pkg.multi_gpu.shard_plan(lib, 1000, 1024, 1, 4, 1)
+    import ctypes as C
+    lo, hi = (C.c_uint32 * 5)(), (C.c_uint32 * 5)()
+    assert lib.dll.b200_shard_plan(C.c_uint32(10), C.c_uint32(16), 4, 4, 1, C.c_double(0), lo, hi) != 0
+    assert lib.dll.b200_shard_plan(C.c_uint32(10), C.c_uint32(16), 0, 4, 2, C.c_double(0), lo, hi) != 0
+    assert lib.dll.b200_shard_plan(C.c_uint32(10), C.c_uint32(16), 0, 4, 1, C.c_double(0), None, hi) != 0

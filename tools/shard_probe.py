@@ -35,7 +35,7 @@ def main():
     inst = bench.load_instance(args.constraints) or bench.make_instance(lib, args.constraints)
     zkey, wtns, _ = inst
     if args.skew > 0:
-        os.environ["B200_SHARD_SKEW"] = repr(args.skew)
+        os.environ["B200_SHARD_SKEW"] = repr(args.skew)  # (used by the uniform plan only)
     for rank in (int(x) for x in args.rank.split(",")):
         cache = pkg.ZKeyCache(lib, zkey, precompute=args.precompute, rank=rank, world=args.world)
         nw = cache.n_vars
@@ -45,7 +45,8 @@ def main():
         first, count = pkg.multi_gpu.owned_polys(rank, args.world)
         lo, hi = cache.h_range()
         mine = torch.zeros((max(count, 1), N, 8), dtype=torch.int32, device="cuda")
-        sl = torch.zeros((3, max(hi - lo, 1), 8), dtype=torch.int32, device="cuda")
+        # random field-sized values: h = a.b - c is then a generic scalar vector, as in a real proof
+        sl = torch.randint(0, 1 << 28, (3, max(hi - lo, 1), 8), dtype=torch.int32, device="cuda")
         ts = []
         for it in range(args.reps + 2):
             torch.cuda.synchronize()
@@ -55,7 +56,7 @@ def main():
             torch.cuda.synchronize()
             if it >= 2:
                 ts.append((time.perf_counter() - t0) * 1e3)
-        print(f"rank {rank}/{args.world} polys {count}: best {min(ts):.3f} ms median {sorted(ts)[len(ts) // 2]:.3f} ms | "
+        print(f"rank {rank}/{args.world} polys {count} ranges {[(hi - lo) for lo, hi in cache.ranges()]}: best {min(ts):.3f} ms median {sorted(ts)[len(ts) // 2]:.3f} ms | "
               f"ntt {tm.ntt_ms:.2f} g1 {tm.msm_g1_ms:.2f} g2 {tm.msm_g2_ms:.2f} total {tm.total_ms:.2f}", flush=True)
         cache.close()
         del mine, sl, w_dev
