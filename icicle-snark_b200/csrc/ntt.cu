@@ -15,8 +15,27 @@ namespace b200 {
     ++g_launches;                                                                                                      \
   } while (0)
 
-  static constexpr int NTT_KMAX = 8;      // log2 of the largest per-pass radix
-  static constexpr int NTT_TILE_LOG = 10; // log2 elements per CTA tile (32 KiB of shared memory)
+  // log2 of the largest per-pass radix and log2 of the elements per CTA tile (32 B each, in shared memory).  Radix-4
+  // stages (two butterfly levels per shared-memory round trip and per barrier) are the default; B200_NTT_VARIANT=0 selects
+  // the radix-2 stage loop, B200_NTT_KMAX / B200_NTT_TILE_LOG the pass structure (tuning knobs, read once).
+  struct NttTuning {
+    int kmax, tile_log, variant;
+  };
+  static const NttTuning& ntt_tuning()
+  {
+    static const NttTuning t = [] {
+      NttTuning v{8, 10, 1};
+      if (const char* e = getenv("B200_NTT_KMAX")) v.kmax = atoi(e);
+      if (const char* e = getenv("B200_NTT_TILE_LOG")) v.tile_log = atoi(e);
+      if (const char* e = getenv("B200_NTT_VARIANT")) v.variant = atoi(e);
+      if (v.kmax < 4) v.kmax = 4; // at most 7 passes up to 2^28 (plan_passes)
+      if (v.kmax > 12) v.kmax = 12;
+      if (v.tile_log < v.kmax) v.tile_log = v.kmax;
+      if (v.tile_log > 12) v.tile_log = 12; // 4096 x 32 B = 128 KiB + the twiddle table
+      return v;
+    }();
+    return t;
+  }
 
   // ------------------------------------------------------------------------------------------------ domain
   static NttDomain g_domains[64];
@@ -210,6 +229,114 @@ namespace b200 {
     }
   }
 
+  template <bool INV>
+  __global__ void __launch_bounds__(512) ntt_pass4_kernel(NttPassArgs a)
+  {
+    extern __shared__ uint4 smem[];
+    const int R = 1 << a.k, M = 1 << a.m;
+    uint4* s = smem;                 // R*M elements
+    uint4* itw = smem + 2 * (R * M); // R/2 internal twiddles w_R^i
+    const int nthreads = blockDim.x, tid = threadIdx.x;
+    const uint32_t nmax = 1u << a.log_nmax;
+    const int log_nr = a.logn - a.k; // log2(N/R)
+    const uint32_t j0 = blockIdx.x << a.m;
+    const uint32_t ns_mask = (1u << a.ns_log) - 1;
+    const Fr* in = a.in + (size_t)blockIdx.y * a.batch_stride;
+    Fr* out = a.out + (size_t)blockIdx.y * a.batch_stride;
+
+    for (int i = tid; i < R / 2; i += nthreads) {
+      uint32_t e = (uint32_t)i << (a.log_nmax - a.k);
+      if (INV && e) e = nmax - e;
+      sts_fr(itw, i, ld_fr(a.tw + e));
+    }
+    const int tw_shift = a.log_nmax - a.ns_log - a.k;
+    for (int e = tid; e < R * M; e += nthreads) {
+      uint32_t t = e >> a.m, jj = e & (M - 1);
+      uint32_t j = j0 + jj;
+      Fr v = ld_fp_coherent(in + ((size_t)j + ((size_t)t << log_nr)) * a.estride);
+      if (a.ns_log > 0) {
+        uint32_t x = ((j & ns_mask) * t) << tw_shift;
+        if (x) {
+          if (INV) x = nmax - x;
+          v = v * ld_fr(a.tw + x);
+        }
+      }
+      sts_fr(s, e, v);
+    }
+    __syncthreads();
+
+    // radix-2 DIF levels taken two at a time: the four elements {t0, t0+q, t0+h, t0+h+q} (h = 2^st, q = h/2) go through
+    // level st (pairs h apart, twiddles w^e0 and w^(e0 + R/4)) and level st-1 (pairs q apart, twiddle w^(2 e0)) in
+    // registers - one shared-memory round trip and one barrier per two levels.  An odd k starts with one radix-2 level.
+    int st = a.k - 1;
+    if (a.k & 1) {
+      const uint32_t half = 1u << st;
+      const int nbf = (R / 2) << a.m;
+      for (int b = tid; b < nbf; b += nthreads) {
+        uint32_t jj = b & (M - 1), bb = b >> a.m;
+        uint32_t lo = bb & (half - 1);
+        uint32_t t = ((bb >> st) << (st + 1)) | lo;
+        int i0 = (t << a.m) + jj, i1 = ((t + half) << a.m) + jj;
+        Fr x = lds_fr(s, i0), y = lds_fr(s, i1);
+        Fr d = x - y;
+        if (st > 0 && lo) d = d * lds_fr(itw, lo << (a.k - 1 - st));
+        sts_fr(s, i0, x + y);
+        sts_fr(s, i1, d);
+      }
+      __syncthreads();
+      --st;
+    }
+    const int nb4 = (R / 4) << a.m;
+    for (; st >= 1; st -= 2) {
+      const uint32_t half = 1u << st, quarter = half >> 1;
+      for (int b = tid; b < nb4; b += nthreads) {
+        uint32_t jj = b & (M - 1), bb = b >> a.m;
+        uint32_t lo = bb & (quarter - 1);
+        uint32_t t0 = ((bb >> (st - 1)) << (st + 1)) | lo;
+        int i0 = (t0 << a.m) + jj, i1 = ((t0 + quarter) << a.m) + jj, i2 = ((t0 + half) << a.m) + jj,
+            i3 = ((t0 + half + quarter) << a.m) + jj;
+        Fr x0 = lds_fr(s, i0), x1 = lds_fr(s, i1), x2 = lds_fr(s, i2), x3 = lds_fr(s, i3);
+        const uint32_t e0 = lo << (a.k - 1 - st);
+        Fr a0 = x0 + x2, a2 = x0 - x2, a1 = x1 + x3, a3 = x1 - x3;
+        if (e0) a2 = a2 * lds_fr(itw, e0);
+        a3 = a3 * lds_fr(itw, e0 + (R >> 2));
+        Fr b0 = a0 + a1, b1 = a0 - a1, b2 = a2 + a3, b3 = a2 - a3;
+        if (e0) { // level st-1: all twiddles are 1 on the last level and for lo == 0
+          Fr w2 = lds_fr(itw, 2 * e0);
+          b1 = b1 * w2;
+          b3 = b3 * w2;
+        }
+        sts_fr(s, i0, b0);
+        sts_fr(s, i1, b1);
+        sts_fr(s, i2, b2);
+        sts_fr(s, i3, b3);
+      }
+      __syncthreads();
+    }
+
+    for (int e = tid; e < R * M; e += nthreads) {
+      uint32_t q, jj;
+      if (a.ns_log == 0) { // first pass: the tile's outputs are one contiguous run, q fastest
+        jj = e >> a.k;
+        q = e & (R - 1);
+      } else {
+        q = e >> a.m;
+        jj = e & (M - 1);
+      }
+      uint32_t j = j0 + jj;
+      size_t idx = ((size_t)(j >> a.ns_log) << (a.ns_log + a.k)) + (j & ns_mask) + ((size_t)q << a.ns_log);
+      uint32_t qr = a.k ? __brev(q) >> (32 - a.k) : 0;
+      Fr v = lds_fr(s, (qr << a.m) + jj);
+      if (a.last) {
+        if (a.post_table)
+          v = v * ld_fr(a.post_table + idx);
+        else if (a.has_scale)
+          v = v * a.scale;
+      }
+      st_fr(out + idx * a.estride, v);
+    }
+  }
+
   // 1-point "transform" and tiny helpers -------------------------------------------------------------
   static __global__ void __launch_bounds__(256)
     bitrev_swap_kernel(Fr* data, int logn, int batch, size_t batch_stride, int estride)
@@ -244,7 +371,8 @@ namespace b200 {
 
   static void plan_passes(int logn, int* ks, int* npass)
   {
-    int np = (logn + NTT_KMAX - 1) / NTT_KMAX;
+    const int kmax = ntt_tuning().kmax;
+    int np = (logn + kmax - 1) / kmax;
     if (np < 1) np = 1;
     int base = logn / np, rem = logn % np;
     for (int i = 0; i < np; ++i)
@@ -306,18 +434,34 @@ namespace b200 {
       a.ns_log = ns_log;
       a.k = ks[p];
       int m = logn - ks[p];
-      if (m > NTT_TILE_LOG - ks[p]) m = NTT_TILE_LOG - ks[p];
+      if (m > ntt_tuning().tile_log - ks[p]) m = ntt_tuning().tile_log - ks[p];
       if (ns_log > 0 && m > ns_log) m = ns_log;
       if (m < 0) m = 0;
       a.m = m;
       a.last = remaining == 0;
       const int tile = 1 << (a.k + a.m);
-      int threads = tile / 2;
-      if (threads > 256) threads = 256;
+      const bool r4 = ntt_tuning().variant != 0;
+      int threads = r4 ? tile / 4 : tile / 2;
+      if (threads > (r4 ? 512 : 256)) threads = r4 ? 512 : 256;
       if (threads < 32) threads = 32;
       dim3 grid((unsigned)(n >> (a.k + a.m)), (unsigned)batch);
       size_t smem = ((size_t)tile + (size_t)(1 << a.k) / 2 + 1) * sizeof(Fr);
-      if (inverse)
+      if (smem > 48 * 1024) { // opt in to large dynamic shared memory once per kernel
+        static std::once_flag once;
+        std::call_once(once, [] {
+          const int cap = 200 * 1024;
+          cudaFuncSetAttribute(ntt_pass_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
+          cudaFuncSetAttribute(ntt_pass_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
+          cudaFuncSetAttribute(ntt_pass4_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
+          cudaFuncSetAttribute(ntt_pass4_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
+        });
+      }
+      if (r4) {
+        if (inverse)
+          B200_LAUNCH(ntt_pass4_kernel<true>, grid, threads, smem, st, a);
+        else
+          B200_LAUNCH(ntt_pass4_kernel<false>, grid, threads, smem, st, a);
+      } else if (inverse)
         B200_LAUNCH(ntt_pass_kernel<true>, grid, threads, smem, st, a);
       else
         B200_LAUNCH(ntt_pass_kernel<false>, grid, threads, smem, st, a);
