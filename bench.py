@@ -4,7 +4,7 @@
   python bench.py [--gpus N] [--steps K] [--warmup W] [--constraints C] [--precompute F]
   python bench.py --impl reference ...        # the reference's own CPU implementation of the path, same instance
   python bench.py --impl reference-cuda ...   # the reference's own CUDA backend rebuilt for sm_100a (oracle/_ref_cuda), same GPU
-  python bench.py --sweep                     # standalone BN254 MSM / NTT sweeps (BASELINE configs[4]) folded into `extras`
+  python bench.py [--no-sweep]                # the standalone BN254 MSM / NTT sweeps (BASELINE configs[4]) are folded into `extras` by default
 
 A "step" is one proof of the synthetic ComplexCircuit(C, C) instance (the reference's benchmark circuit,
 benchmark/3200k/circuit.circom; valid .zkey/.wtns from a seeded known-toxic-waste setup, tools/synth.py -
@@ -313,7 +313,8 @@ def main():
     ap.add_argument("--precompute", type=int, default=int(os.environ.get("B200_PRECOMPUTE", "16")))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-verify", action="store_true", help="skip the pairing checks of the last timed proof (debug only)")
-    ap.add_argument("--sweep", action="store_true", help="add the standalone MSM / NTT sweeps (configs[4]) to `extras`")
+    ap.add_argument("--sweep", action="store_true", help="(default) add the standalone MSM / NTT sweeps (configs[4]) to `extras`")
+    ap.add_argument("--no-sweep", action="store_true", help="skip the standalone MSM / NTT sweeps")
     ap.add_argument("--split-quotient", type=int, default=1, help="N>1: split the three quotient polynomials across ranks (0 = replicate)")
     ap.add_argument("--exchange", default="lib", choices=["lib", "torch"],
                     help="N>1: who moves the data: 'lib' = b200_groth16_prove_sharded (NCCL inside the C library, no host in the "
@@ -550,7 +551,7 @@ def main():
     extras["msm_g1_mpoints_s"] = n_msm / (sum(t_ms) / len(t_ms)) / 1e3
     extras["msm_g1_size"] = n_msm
     extras["msm_g1_plan"] = plan_info(lib, n_msm, 1)
-    if args.sweep:
+    if not args.no_sweep:
         from tools import sweep
         extras["sweep"] = sweep.run(lib, pkg, log=log)
 

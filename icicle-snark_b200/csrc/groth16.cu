@@ -347,6 +347,24 @@ namespace b200 {
     return sp;
   }
 
+  // The prover's transforms must run over the subgroup generated by host_omega(power): the coset powers (keys) and the
+  // zkey's H points are tied to it.  A global domain initialised by another caller is reused only when it is large enough
+  // AND its root squares down to that generator; otherwise it is replaced (bn254_ntt_init_domain accepts any primitive root).
+  static eIcicleError ensure_prover_domain(uint32_t power, cudaStream_t st)
+  {
+    const NttDomain* d = ntt_domain();
+    bool ok = d && d->max_log >= (int)power;
+    if (ok) {
+      Fr w = Fr::to_mont(d->root_std);
+      for (int i = d->max_log; i > (int)power; --i)
+        w = w.sqr();
+      ok = (w == Fr::to_mont(host_omega((int)power)));
+    }
+    if (ok) return ICICLE_SUCCESS;
+    if (d) bn254_ntt_release_domain();
+    return ntt_init_domain_host(host_omega((int)power), st);
+  }
+
   static void cache_free(b200_zkey_cache* c)
   {
     if (!c) return;
@@ -731,11 +749,7 @@ namespace b200 {
 
     // ---- NTT domain of order N (cache.rs:242-256 sizes it from points_a.len(); domain_size is what the
     //      transforms need - SURVEY App. C). A larger existing domain is kept; a smaller one is replaced.
-    {
-      const NttDomain* d = ntt_domain();
-      if (d && d->max_log < (int)c->power) bn254_ntt_release_domain();
-      if ((err = ntt_init_domain_host(host_omega((int)c->power), st)) != ICICLE_SUCCESS) return fail(err);
-    }
+    if ((err = ensure_prover_domain(c->power, st)) != ICICLE_SUCCESS) return fail(err);
 
     // ---- workspace
     c->wit_slice = ((size_t)c->n_vars + world - 1) / world;
@@ -783,11 +797,7 @@ namespace b200 {
     B200_CUDA(cudaSetDevice(c->device), ICICLE_INVALID_DEVICE);
     // CacheManager::get_cache re-initialises the NTT domain on every proof (cache.rs:242-256): a no-op unless
     // someone released or shrank it in between
-    {
-      const NttDomain* d = ntt_domain();
-      if (d && d->max_log < (int)c->power) bn254_ntt_release_domain();
-      if (!d || d->max_log < (int)c->power) B200_TRY(ntt_init_domain_host(host_omega((int)c->power), c->s_copy));
-    }
+    B200_TRY(ensure_prover_domain(c->power, c->s_copy));
     B200_CUDA(cudaEventRecord(c->ev_start, c->s_copy), ICICLE_UNKNOWN_FALLBACK);
     if (full && c->world > 1 && c->ev_slice && c->w_hi > c->w_lo) {
       // sharded rank that also evaluates R1CS rows: its own slice first - the witness MSMs (s_g1, s_g2) start on it
@@ -1336,11 +1346,7 @@ eIcicleError b200_groth16_prove_sharded(
   if (world > 1 && wit_on_host && c->wit_slice > 0) { // (every rank must pass the same kind of memory: this is a collective)
     if (n_witness != c->n_vars) return ICICLE_INVALID_ARGUMENT;
     const size_t sl = c->wit_slice, lo = std::min((size_t)rank * sl, (size_t)c->n_vars), hi = std::min(lo + sl, (size_t)c->n_vars);
-    {
-      const NttDomain* d = ntt_domain();
-      if (d && d->max_log < (int)c->power) bn254_ntt_release_domain();
-      if (!d || d->max_log < (int)c->power) B200_TRY(ntt_init_domain_host(host_omega((int)c->power), c->s_copy));
-    }
+    B200_TRY(ensure_prover_domain(c->power, c->s_copy));
     cudaEventRecord(c->ev_start, c->s_copy);
     if (hi > lo && cudaMemcpyAsync(c->d_witness + lo, witness + lo, (hi - lo) * 32, cudaMemcpyDefault, c->s_copy) != cudaSuccess)
       e = ICICLE_COPY_FAILED;

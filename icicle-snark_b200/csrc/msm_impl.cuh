@@ -504,12 +504,16 @@ namespace b200 {
     if (host_scalars) per_point += 2 * 32;                             // double-buffered staging
     if (host_points) per_point += 2 * affine_bytes * (size_t)f;
     if (mont_copy) per_point += affine_bytes * (size_t)f;
-    size_t free_b = 0, total_b = 0;
-    if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
-      const size_t fixed = (size_t)full.nbuckets * (4 * 8 + 2 * sizeof(MsmItem) + 3 * 2 * affine_bytes); // offsets, items, buckets
-      const size_t budget = (size_t)(0.7 * (double)free_b);
-      const size_t by_mem = budget > fixed ? (budget - fixed) / per_point : 1;
-      if (by_mem < lim) lim = by_mem;
+    // device memory: only problems that could matter are worth a driver query (cudaMemGetInfo is not free, and small MSMs
+    // are latency-sensitive): below 8 GiB of estimated need the answer cannot change the plan on a 180 GB part
+    const size_t fixed = (size_t)full.nbuckets * (4 * 8 + 2 * sizeof(MsmItem) + 3 * 2 * affine_bytes); // offsets, items, buckets
+    if (fixed + per_point * (size_t)full.n > ((size_t)8 << 30)) {
+      size_t free_b = 0, total_b = 0;
+      if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
+        const size_t budget = (size_t)(0.7 * (double)free_b);
+        const size_t by_mem = budget > fixed ? (budget - fixed) / per_point : 1;
+        if (by_mem < lim) lim = by_mem;
+      }
     }
     if (const char* e = getenv("B200_MSM_CHUNK")) {
       const long long v = atoll(e);

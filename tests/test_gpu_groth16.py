@@ -341,3 +341,27 @@ def test_sparse_b_columns_are_dropped_and_proofs_unchanged(gpu, ref, monkeypatch
         assert pkg.proof_json(p) == G.proof_json(proof_ref)
     finally:
         cache.close()
+
+
+def test_foreign_ntt_domain_is_replaced(gpu, ref):
+    """bn254_ntt_init_domain accepts ANY primitive root; the prover's coset powers and the zkey's H points are tied to the
+    standard generator.  A global domain that another caller initialised with a different root (here: the cube of the
+    standard one - also primitive, large enough) must not be reused: the proof stays byte-identical to the golden file."""
+    zkey, wtns, vk, gold11, goldrs, _ = load(100)
+    w = wtns_words(wtns)
+    gpu.ntt_release_domain()
+    std = gpu.get_root_of_unity(1 << 12)
+    cube = gpu.fr_mul(gpu.fr_mul(std, std), std)
+    gpu.ntt_init_domain(cube)
+    try:
+        cache = pkg.ZKeyCache(gpu, zkey)
+        try:
+            assert pkg.proof_json(cache.prove(w, FIXED_R, FIXED_S)[0]) == goldrs
+            # ... and again when the foreign domain appears between two proofs on a warm cache
+            gpu.ntt_release_domain()
+            gpu.ntt_init_domain(cube)
+            assert pkg.proof_json(cache.prove(w, 1, 1)[0]) == gold11
+        finally:
+            cache.close()
+    finally:
+        gpu.ntt_release_domain()
