@@ -355,7 +355,113 @@ namespace b200 {
 
 } // namespace b200
 #include "msm_batch_affine.cuh"
+#include "msm_reduce_quad.cuh"
 namespace b200 {
+
+  // ---- quad-cooperative variants of the reduction kernels (msm_reduce_quad.cuh): one quad per running-sum chunk ----
+  inline bool reduce_quad_enabled()
+  {
+    static const bool on = [] {
+      const char* e = getenv("B200_MSM_QUAD");
+      return !(e && e[0] == '0');
+    }();
+    return on;
+  }
+
+  template <class F>
+  __global__ void __launch_bounds__(128) msm_reduce_chunks_quad_kernel(
+    MsmDev pl, int nsel, const uint32_t* offsets, const XYZZ<F>* buckets, XYZZ<F>* chunk_sums, XYZZ<F>* chunk_runs, int out_stride)
+  {
+    int chunks_per_set = pl.bpw / REDUCE_CHUNK;
+    if (chunks_per_set == 0) chunks_per_set = 1;
+    int chunk_len = pl.bpw < REDUCE_CHUNK ? pl.bpw : REDUCE_CHUNK;
+    int per_msm = pl.sets * chunks_per_set;
+    int total = nsel * per_msm;
+    const int ql = threadIdx.x & 3;
+    const unsigned qm = 0xFu << (threadIdx.x & 28);
+    for (int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 2; t < total; t += (gridDim.x * blockDim.x) >> 2) {
+      int which = t / per_msm, r = t - which * per_msm;
+      int set = r / chunks_per_set, q = r - set * chunks_per_set;
+      size_t key0 = (size_t)set * pl.bpw + (size_t)q * chunk_len;
+      const XYZZ<F>* b = buckets + (size_t)which * pl.nbuckets + key0;
+      const uint32_t* off = offsets + key0;
+      XYZZ<F> run = XYZZ<F>::inf(), tot = XYZZ<F>::inf();
+      for (int j = chunk_len - 1; j >= 0; --j) {
+        if (off[j + 1] != off[j]) xyzz_add_quad(run, ld_struct(b + j), ql, qm); // empty buckets were never written
+        xyzz_add_quad(tot, run, ql, qm);
+      }
+      if (ql == 0) {
+        st_struct(chunk_sums + (size_t)(which * pl.sets + set) * out_stride + q, tot);
+        if (chunks_per_set > 1) st_struct(chunk_runs + t, run);
+      }
+    }
+  }
+
+  template <class F>
+  __global__ void __launch_bounds__(128) msm_reduce_level1_quad_kernel(
+    int nsets, int chunks_per_set, int l0_log, const XYZZ<F>* chunk_runs, XYZZ<F>* chunk_sums, int out_stride)
+  {
+    const int l2 = chunks_per_set < REDUCE_CHUNK ? chunks_per_set : REDUCE_CHUNK;
+    const int chunks2 = chunks_per_set / l2;
+    const int total = nsets * chunks2;
+    const int ql = threadIdx.x & 3;
+    const unsigned qm = 0xFu << (threadIdx.x & 28);
+    for (int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 2; t < total; t += (gridDim.x * blockDim.x) >> 2) {
+      int set = t / chunks2, q2 = t - set * chunks2;
+      const XYZZ<F>* r = chunk_runs + (size_t)set * chunks_per_set + (size_t)q2 * l2;
+      XYZZ<F> run = XYZZ<F>::inf(), tot = XYZZ<F>::inf();
+      for (int j = l2 - 1; j >= 0; --j) {
+        xyzz_add_quad(run, ld_struct(r + j), ql, qm);
+        xyzz_add_quad(tot, run, ql, qm);
+      }
+      // tot = sum (j+1) R0_j ; wanted: sum (q2 l2 + j) R0_j = tot + (q2 l2 - 1) run
+      uint32_t base = (uint32_t)q2 * l2;
+      if (base) {
+        XYZZ<F> m = XYZZ<F>::inf();
+        for (int bit = 31 - __clz(base); bit >= 0; --bit) {
+          xyzz_dbl_quad(m, ql, qm);
+          if ((base >> bit) & 1) xyzz_add_quad(m, run, ql, qm);
+        }
+        xyzz_add_quad(tot, m, ql, qm);
+      }
+      xyzz_add_quad(tot, run.neg(), ql, qm);
+      for (int k = 0; k < l0_log; ++k)
+        xyzz_dbl_quad(tot, ql, qm);
+      if (ql == 0) st_struct(chunk_sums + (size_t)set * out_stride + chunks_per_set + q2, tot);
+    }
+  }
+
+  // sums `per_cta` consecutive values per CTA like msm_set_sum_kernel: the 32 quads of the CTA take strided values, then a
+  // tree over the quads' partial sums in shared memory
+  template <class F>
+  __global__ void __launch_bounds__(WSUM_BLOCK)
+    msm_set_sum_quad_kernel(const XYZZ<F>* in, int per_set, int per_cta, XYZZ<F>* out)
+  {
+    extern __shared__ uint4 smem_raw[];
+    XYZZ<F>* sh = reinterpret_cast<XYZZ<F>*>(smem_raw);
+    constexpr int NQ = WSUM_BLOCK / 4;
+    const int ql = threadIdx.x & 3, qi = threadIdx.x >> 2;
+    const unsigned qm = 0xFu << (threadIdx.x & 28);
+    int beg = blockIdx.x * per_cta;
+    int cnt = per_set - beg < per_cta ? per_set - beg : per_cta;
+    if (cnt < 0) cnt = 0;
+    const XYZZ<F>* src = in + (size_t)blockIdx.y * per_set + beg;
+    XYZZ<F> acc = XYZZ<F>::inf();
+    for (int i = qi; i < cnt; i += NQ)
+      xyzz_add_quad(acc, ld_struct(src + i), ql, qm);
+    if (ql == 0) sh[qi] = acc;
+    __syncthreads();
+    for (int s = NQ / 2; s > 0; s >>= 1) {
+      if (qi < s) {
+        XYZZ<F> a = sh[qi];
+        xyzz_add_quad(a, sh[qi + s], ql, qm);
+        if (ql == 0) sh[qi] = a;
+      }
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) st_struct(out + (size_t)blockIdx.y * gridDim.x + blockIdx.x, sh[0]);
+  }
+
 
   // ------------------------------------------------------------------------------------------------
   template <class F>
@@ -420,13 +526,27 @@ namespace b200 {
         sorted.item_off, partials, buckets, (uint32_t)nb, (uint32_t)max_items);
     }
     msm_profile_end(st, plan, sizeof(F) > sizeof(Fq) ? 1 : 0, nsel, ba_rounds);
-    B200_LAUNCH(
-      msm_reduce_chunks_kernel<F>, grid_for((size_t)nsets * chunks_per_set, 128, 16), 128, 0, st, pl, nsel, sorted.offsets, buckets,
-      chunk_sums, chunk_runs, sum_stride);
-    if (chunks2 > 0)
+    // Level 0 is multiplier work when there are many chunks (one thread each); with few it is a latency chain like the
+    // levels above it, which always run quad-cooperatively (msm_reduce_quad.cuh)
+    const bool quad = reduce_quad_enabled();
+    if (quad && (size_t)nsets * chunks_per_set <= 32768)
       B200_LAUNCH(
-        msm_reduce_level1_kernel<F>, grid_for((size_t)nsets * chunks2, 128, 16), 128, 0, st, nsets, chunks_per_set, l0_log, chunk_runs,
-        chunk_sums, sum_stride);
+        msm_reduce_chunks_quad_kernel<F>, grid_for((size_t)nsets * chunks_per_set * 4, 128, 16), 128, 0, st, pl, nsel, sorted.offsets,
+        buckets, chunk_sums, chunk_runs, sum_stride);
+    else
+      B200_LAUNCH(
+        msm_reduce_chunks_kernel<F>, grid_for((size_t)nsets * chunks_per_set, 128, 16), 128, 0, st, pl, nsel, sorted.offsets, buckets,
+        chunk_sums, chunk_runs, sum_stride);
+    if (chunks2 > 0) {
+      if (quad)
+        B200_LAUNCH(
+          msm_reduce_level1_quad_kernel<F>, grid_for((size_t)nsets * chunks2 * 4, 128, 16), 128, 0, st, nsets, chunks_per_set, l0_log,
+          chunk_runs, chunk_sums, sum_stride);
+      else
+        B200_LAUNCH(
+          msm_reduce_level1_kernel<F>, grid_for((size_t)nsets * chunks2, 128, 16), 128, 0, st, nsets, chunks_per_set, l0_log, chunk_runs,
+          chunk_sums, sum_stride);
+    }
     {
       // level 1: G CTAs per set, level 2: one CTA per set over the G partial sums
       int G = (sum_stride + WSUM_BLOCK * 4 - 1) / (WSUM_BLOCK * 4);
@@ -434,7 +554,14 @@ namespace b200 {
       if (G < 1) G = 1;
       int per_cta = (sum_stride + G - 1) / G;
       const size_t sm = WSUM_BLOCK * sizeof(XYZZ<F>);
-      if (G == 1) {
+      if (quad) {
+        if (G == 1) {
+          B200_LAUNCH(msm_set_sum_quad_kernel<F>, dim3(1, nsets), WSUM_BLOCK, sm, st, chunk_sums, sum_stride, sum_stride, set_sums);
+        } else {
+          B200_LAUNCH(msm_set_sum_quad_kernel<F>, dim3(G, nsets), WSUM_BLOCK, sm, st, chunk_sums, sum_stride, per_cta, partials);
+          B200_LAUNCH(msm_set_sum_quad_kernel<F>, dim3(1, nsets), WSUM_BLOCK, sm, st, partials, G, G, set_sums);
+        }
+      } else if (G == 1) {
         B200_LAUNCH(msm_set_sum_kernel<F>, dim3(1, nsets), WSUM_BLOCK, sm, st, chunk_sums, sum_stride, sum_stride, set_sums);
       } else {
         B200_LAUNCH(msm_set_sum_kernel<F>, dim3(G, nsets), WSUM_BLOCK, sm, st, chunk_sums, sum_stride, per_cta, partials);
