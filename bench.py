@@ -436,6 +436,12 @@ def main():
     # device-side phase times of the last proof (CUDA events inside the library)
     phases = {k: round(getattr(tm, k), 3) for k in ("h2d_ms", "r1cs_ms", "ntt_ms", "msm_g1_ms", "msm_g2_ms", "total_ms")}
 
+    # standalone sweeps at N > 1 are collective (sharded MSM through the library's communicator): every rank runs them
+    # here, before the other ranks retire; at N = 1 they run with the other extras below
+    sweep_results = None
+    if world > 1 and not args.no_sweep:
+        from tools import sweep
+        sweep_results = sweep.run(lib, pkg, log=log if rank == 0 else None)
     if rank != 0:
         if world > 1:
             dist.barrier()
@@ -551,7 +557,9 @@ def main():
     extras["msm_g1_mpoints_s"] = n_msm / (sum(t_ms) / len(t_ms)) / 1e3
     extras["msm_g1_size"] = n_msm
     extras["msm_g1_plan"] = plan_info(lib, n_msm, 1)
-    if not args.no_sweep:
+    if sweep_results is not None:
+        extras["sweep"] = sweep_results
+    elif not args.no_sweep:
         from tools import sweep
         extras["sweep"] = sweep.run(lib, pkg, log=log)
 
