@@ -68,3 +68,35 @@ extern "C" int b200_inv_check(int n, uint64_t seed, int field_fq, int device)
 {
   return field_fq ? check<Fq>(n, seed, device) : check<Fr>(n, seed, device);
 }
+
+// host_double_scalar_mul (csrc/host_math.h: the Shamir double-scalar multiplication of the prover's epilogue) against two
+// plain double-and-add multiplications, on random points k*G and scalars incl. 0, 1, equal points and opposite points.
+// Returns the number of mismatches.
+#include "host_math.h"
+extern "C" int b200_double_mul_check(int iters, uint64_t seed)
+{
+  int bad = 0;
+  uint64_t s = seed | 1;
+  const G1XYZZ g = G1XYZZ::from_affine(g1_generator_mont());
+  for (int it = 0; it < iters; ++it) {
+    Fr k1 = Fr::from_mont(sample<Fr>(s, -1)), k2 = Fr::from_mont(sample<Fr>(s, -1)), a = Fr::from_mont(sample<Fr>(s, -1)),
+       b = Fr::from_mont(sample<Fr>(s, -1));
+    if (it == 0) k1 = Fr::zero();
+    if (it == 1) { k2 = Fr::zero(); k2.v[0] = 1; }
+    G1XYZZ p = host_scalar_mul(g, a), q = host_scalar_mul(g, b);
+    if (it == 2) q = p;
+    if (it == 3) q = p.neg();
+    if (it == 4) q = G1XYZZ::inf();
+    G1XYZZ want = host_scalar_mul(p, k1);
+    want.add(host_scalar_mul(q, k2));
+    G1XYZZ got = host_double_scalar_mul(p, k1, q, k2);
+    const bool wi = want.is_inf(), gi = got.is_inf();
+    if (wi != gi) {
+      ++bad;
+    } else if (!wi) {
+      Affine<Fq> x = want.to_affine(), y = got.to_affine();
+      if (!(x.x == y.x) || !(x.y == y.y)) ++bad;
+    }
+  }
+  return bad;
+}

@@ -296,7 +296,23 @@ def test_msm_suite_with_batched_affine_forced():
     if os.environ.get("B200_BATCH_AFFINE") == "3":
         pytest.skip("already inside the forced run")
     env = dict(os.environ, B200_BATCH_AFFINE="3")
-    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-m", "gpu", "-x", "-q", "-k", "msm and not forced"],
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-m", "gpu", "-x", "-q", "-k", "msm and not forced and not thread_per_chunk"],
+                       env=env, capture_output=True, text=True, timeout=1200, cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+
+
+def test_msm_suite_with_thread_per_chunk_reduction():
+    """The bucket reduction's upper levels run quad-cooperatively by default (csrc/msm_reduce_quad.cuh); B200_MSM_QUAD=0
+    selects the one-thread-per-chunk kernels (still the level-0 path of large MSMs).  Same parity suite, read once per
+    process, hence the subprocess."""
+    import os
+    import subprocess
+    import sys
+    if os.environ.get("B200_MSM_QUAD") == "0":
+        pytest.skip("already inside the forced run")
+    env = dict(os.environ, B200_MSM_QUAD="0")
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-m", "gpu", "-x", "-q", "-k",
+                        "msm and not forced and not thread_per_chunk and not chunked"],
                        env=env, capture_output=True, text=True, timeout=1200, cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
 

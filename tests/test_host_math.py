@@ -98,3 +98,13 @@ def test_division_step_inverse_matches_fermat_on_host(lib, fq):
     f = pkg.tools_lib().b200_inv_check
     f.argtypes = [C.c_int, C.c_uint64, C.c_int, C.c_int]
     assert f(3000, 20261017 + fq, fq, 0) == 0
+
+
+def test_epilogue_double_scalar_multiplication_on_host(lib):
+    """csrc/host_math.h host_double_scalar_mul (s*pi_a + r*pi_b1 of the blinding epilogue, proof_helper.rs:274-295, with one
+    shared doubling chain) == two plain double-and-add multiplications; zero / one scalars, equal, opposite and infinite points."""
+    import ctypes as C
+    import icicle_snark_b200 as pkg
+    f = pkg.tools_lib().b200_double_mul_check
+    f.argtypes = [C.c_int, C.c_uint64]
+    assert f(40, 20261017) == 0
