@@ -427,6 +427,10 @@ def main():
         return float(t.item())
 
     ms_dev, ms_e2e = agg(per_dev), agg(per_e2e)
+    # the same call with a PAGEABLE host witness (what a Rust Vec or an mmap'd .wtns is): staged through pinned memory by the library
+    w_pageable = np.ascontiguousarray(w_np).copy()
+    per_pg, (proof_pg, _) = timed(w_pageable.ctypes.data, max(3, args.steps // 2), 1)
+    ms_e2e_pageable = agg(per_pg)
     if world > 1 and (qx is not None or comm is not None):
         # cross-check of the split path: the replicated-chain proof (same r, s) must be identical
         parts_r, _ = cache.commit_partials(w_dev.data_ptr(), n_witness=nw)
@@ -509,7 +513,8 @@ def main():
                       "launches": [{k: r[k] for k in ("g2", "nsel", "n", "windows", "c", "batched", "ms")} for r in recs]},
         }
 
-    extras = {"device_cache_bytes": cache.device_bytes, "cache_build_s": round(t_cache, 3)}
+    assert pkg.proof_json(proof_pg) == pkg.proof_json(proof), "pageable-witness proof differs"
+    extras = {"device_cache_bytes": cache.device_bytes, "cache_build_s": round(t_cache, 3), "e2e_pageable_witness_ms": ms_e2e_pageable}
     # ---- the drop-in call itself: b200_groth16_prove_files (pageable mmap'd witness, JSON written), warm cache
     if world == 1:
         try:

@@ -33,6 +33,8 @@
 #include <sys/mman.h>
 #include <sys/stat.h>
 #include <unistd.h>
+#include <atomic>
+#include <thread>
 #include <chrono>
 #include <cmath>
 #include <vector>
@@ -202,6 +204,7 @@ struct b200_zkey_cache {
   Fr* qx_slices = nullptr;
   uint8_t *d_all_parts = nullptr, *h_all_parts = nullptr;
   cudaEvent_t ev_slice = nullptr, ev_xch = nullptr;
+  uint8_t* h_stage = nullptr; // pinned staging for a pageable host witness (copy_pageable), n_vars * 32 B, lazily allocated
   size_t wit_slice = 0; // d_witness holds world * wit_slice elements (>= n_vars): in-place all-gather of the uploaded slices
 };
 
@@ -382,6 +385,7 @@ namespace b200 {
     }
     if (c->h_results) cudaFreeHost(c->h_results);
     if (c->h_all_parts) cudaFreeHost(c->h_all_parts);
+    if (c->h_stage) cudaFreeHost(c->h_stage);
     if (c->ev_slice) cudaEventDestroy(c->ev_slice);
     if (c->ev_xch) cudaEventDestroy(c->ev_xch);
     cudaStream_t ss[] = {c->s_copy, c->s_g1, c->s_g2, c->s_g3, c->s_q};
@@ -608,8 +612,11 @@ namespace b200 {
     }
     {
       // which signals of a range have a B point at all? (B1 and B2 are zero together: same v_s(tau))
-      auto keep_list = [&](uint32_t lo, uint32_t hi) {
-        std::vector<uint32_t> keep;
+      std::map<std::pair<uint32_t, uint32_t>, std::vector<uint32_t>> keep_memo; // one scan per distinct range
+      auto keep_list = [&](uint32_t lo, uint32_t hi) -> const std::vector<uint32_t>& {
+        auto it = keep_memo.find({lo, hi});
+        if (it != keep_memo.end()) return it->second;
+        std::vector<uint32_t>& keep = keep_memo[{lo, hi}];
         keep.reserve(hi - lo);
         const uint64_t* b1 = reinterpret_cast<const uint64_t*>(sec[6].p) + (size_t)lo * 8;
         const uint64_t* b2 = reinterpret_cast<const uint64_t*>(sec[7].p) + (size_t)lo * 16;
@@ -788,6 +795,56 @@ namespace b200 {
     return {r_a, r_a + 1, r_a + 2, r_a + 3, (G2Projective*)(c->d_results + 4 * 96)};
   }
 
+  // Host -> device copy of [lo, hi) of the witness on s_copy.  A pageable source (a Rust Vec, an mmap'd .wtns: what the
+  // reference's callers pass) would be staged by the driver at ~12 GB/s on one thread; instead four threads copy 4 MiB
+  // chunks into a pinned buffer and each chunk's DMA is queued as soon as it is complete, so the copy into pinned memory
+  // overlaps the transfer.  Pinned, registered and device sources take the direct path.  B200_STAGE_MIN_BYTES (default
+  // 4 MiB) is the size from which staging pays.
+  static eIcicleError copy_witness_range(b200_zkey_cache* c, const bn254_scalar_t* witness, size_t lo, size_t hi)
+  {
+    if (hi <= lo) return ICICLE_SUCCESS;
+    const size_t bytes = (hi - lo) * 32;
+    const char* mb_env = getenv("B200_STAGE_MIN_BYTES");
+    const size_t min_bytes = mb_env ? (size_t)atoll(mb_env) : (size_t)4 << 20;
+    bool pageable = false;
+    if (bytes >= min_bytes) {
+      cudaPointerAttributes pa;
+      pageable = cudaPointerGetAttributes(&pa, witness) != cudaSuccess || pa.type == cudaMemoryTypeUnregistered;
+      (void)cudaGetLastError();
+    }
+    if (pageable && !c->h_stage && cudaHostAlloc((void**)&c->h_stage, (size_t)c->n_vars * 32, cudaHostAllocDefault) != cudaSuccess) {
+      (void)cudaGetLastError();
+      c->h_stage = nullptr;
+      pageable = false; // no pinned memory to be had: let the driver stage it
+    }
+    if (!pageable) {
+      B200_CUDA(cudaMemcpyAsync(c->d_witness + lo, witness + lo, bytes, cudaMemcpyDefault, c->s_copy), ICICLE_COPY_FAILED);
+      return ICICLE_SUCCESS;
+    }
+    const size_t chunk = (size_t)4 << 20;
+    const size_t n_chunks = (bytes + chunk - 1) / chunk;
+    const int n_threads = (int)std::min<size_t>(4, n_chunks);
+    const uint8_t* src = reinterpret_cast<const uint8_t*>(witness + lo);
+    uint8_t* stage = c->h_stage + lo * 32;
+    uint8_t* dst = reinterpret_cast<uint8_t*>(c->d_witness + lo);
+    std::atomic<int> failed(0);
+    auto work = [&](int t) {
+      if (cudaSetDevice(c->device) != cudaSuccess) failed = 1;
+      for (size_t k = (size_t)t; k < n_chunks && !failed; k += (size_t)n_threads) {
+        const size_t off = k * chunk, len = std::min(chunk, bytes - off);
+        memcpy(stage + off, src + off, len);
+        if (cudaMemcpyAsync(dst + off, stage + off, len, cudaMemcpyHostToDevice, c->s_copy) != cudaSuccess) failed = 1;
+      }
+    };
+    std::vector<std::thread> pool;
+    for (int t = 1; t < n_threads; ++t)
+      pool.emplace_back(work, t);
+    work(0);
+    for (auto& th : pool)
+      th.join();
+    return failed ? ICICLE_COPY_FAILED : ICICLE_SUCCESS;
+  }
+
   // witness H2D (proof_helper.rs:194-196); every compute stream waits on it
   // (full == false: a rank that evaluates no R1CS rows only needs the witness slice its MSM shard reads)
   static eIcicleError enqueue_upload(b200_zkey_cache* c, const bn254_scalar_t* witness, uint32_t n_witness, bool full = true)
@@ -802,26 +859,18 @@ namespace b200 {
     if (full && c->world > 1 && c->ev_slice && c->w_hi > c->w_lo) {
       // sharded rank that also evaluates R1CS rows: its own slice first - the witness MSMs (s_g1, s_g2) start on it
       // while the rest of the witness, which only the quotient chain reads, is still crossing PCIe
-      B200_CUDA(
-        cudaMemcpyAsync(c->d_witness + c->w_lo, witness + c->w_lo, (size_t)(c->w_hi - c->w_lo) * 32, cudaMemcpyDefault, c->s_copy),
-        ICICLE_COPY_FAILED);
+      B200_TRY(copy_witness_range(c, witness, c->w_lo, c->w_hi));
       B200_CUDA(cudaEventRecord(c->ev_slice, c->s_copy), ICICLE_UNKNOWN_FALLBACK);
       for (cudaStream_t s : {c->s_g1, c->s_g2, c->s_g3})
         B200_CUDA(cudaStreamWaitEvent(s, c->ev_slice, 0), ICICLE_UNKNOWN_FALLBACK);
-      if (c->w_lo > 0)
-        B200_CUDA(cudaMemcpyAsync(c->d_witness, witness, (size_t)c->w_lo * 32, cudaMemcpyDefault, c->s_copy), ICICLE_COPY_FAILED);
-      if (c->w_hi < c->n_vars)
-        B200_CUDA(
-          cudaMemcpyAsync(c->d_witness + c->w_hi, witness + c->w_hi, (size_t)(c->n_vars - c->w_hi) * 32, cudaMemcpyDefault, c->s_copy),
-          ICICLE_COPY_FAILED);
+      B200_TRY(copy_witness_range(c, witness, 0, c->w_lo));
+      B200_TRY(copy_witness_range(c, witness, c->w_hi, c->n_vars));
       B200_CUDA(cudaEventRecord(c->ev_h2d, c->s_copy), ICICLE_UNKNOWN_FALLBACK);
       B200_CUDA(cudaStreamWaitEvent(c->s_q, c->ev_h2d, 0), ICICLE_UNKNOWN_FALLBACK);
       return ICICLE_SUCCESS;
     }
     const size_t w_lo = full ? 0 : c->w_lo, w_hi = full ? c->n_vars : c->w_hi;
-    if (w_hi > w_lo)
-      B200_CUDA(
-        cudaMemcpyAsync(c->d_witness + w_lo, witness + w_lo, (w_hi - w_lo) * 32, cudaMemcpyDefault, c->s_copy), ICICLE_COPY_FAILED);
+    B200_TRY(copy_witness_range(c, witness, w_lo, w_hi));
     B200_CUDA(cudaEventRecord(c->ev_h2d, c->s_copy), ICICLE_UNKNOWN_FALLBACK);
     for (cudaStream_t s : {c->s_g1, c->s_g2, c->s_g3, c->s_q})
       B200_CUDA(cudaStreamWaitEvent(s, c->ev_h2d, 0), ICICLE_UNKNOWN_FALLBACK);
@@ -1348,8 +1397,7 @@ eIcicleError b200_groth16_prove_sharded(
     const size_t sl = c->wit_slice, lo = std::min((size_t)rank * sl, (size_t)c->n_vars), hi = std::min(lo + sl, (size_t)c->n_vars);
     B200_TRY(ensure_prover_domain(c->power, c->s_copy));
     cudaEventRecord(c->ev_start, c->s_copy);
-    if (hi > lo && cudaMemcpyAsync(c->d_witness + lo, witness + lo, (hi - lo) * 32, cudaMemcpyDefault, c->s_copy) != cudaSuccess)
-      e = ICICLE_COPY_FAILED;
+    e = copy_witness_range(c, witness, lo, hi);
     if (e == ICICLE_SUCCESS &&
         nccl().AllGather(c->d_witness + (size_t)rank * sl, c->d_witness, sl * 32, ncclUint8, comm->comm, c->s_copy) != ncclSuccess)
       e = (eIcicleError)ICICLE_UNKNOWN_FALLBACK;

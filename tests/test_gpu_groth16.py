@@ -365,3 +365,31 @@ def test_foreign_ntt_domain_is_replaced(gpu, ref):
             cache.close()
     finally:
         gpu.ntt_release_domain()
+
+
+def test_pageable_witness_takes_the_staged_upload(gpu, tmp_path, monkeypatch):
+    """A pageable host witness (numpy memory, an mmap'd .wtns) is copied through the pinned staging buffer by several
+    threads in chunks (copy_witness_range); forced on at test sizes.  Same proofs as the direct path, on one device and on
+    sharded caches (slice-first upload), through the struct API and the file-level API."""
+    zkey, wtns, vk, gold11, goldrs, _ = load(100)
+    w = wtns_words(wtns)
+    monkeypatch.setenv("B200_STAGE_MIN_BYTES", "64")
+    cache = pkg.ZKeyCache(gpu, zkey, precompute=4)
+    try:
+        for _ in range(2):
+            assert pkg.proof_json(cache.prove(w, FIXED_R, FIXED_S)[0]) == goldrs
+    finally:
+        cache.close()
+    caches = [pkg.ZKeyCache(gpu, zkey, rank=r, world=3) for r in range(3)]
+    try:
+        parts = [c.commit_partials(w)[0] for c in caches]
+        assert pkg.proof_json(caches[0].finish(parts, 1, 1)) == gold11
+    finally:
+        for c in caches:
+            c.close()
+    base = os.path.join(GOLD, "complex_100")
+    monkeypatch.setenv("B200_NO_RANDOMNESS", "1")
+    proof_p, public_p = str(tmp_path / "proof.json"), str(tmp_path / "public.json")
+    assert gpu.dll.b200_groth16_prove_files((base + ".wtns").encode(), (base + ".zkey").encode(), proof_p.encode(),
+                                            public_p.encode(), b"CUDA") == 0
+    assert open(proof_p).read() == open(base + ".proof_r1s1.json").read()
