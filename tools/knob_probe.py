@@ -3,7 +3,7 @@
 a fresh ZKeyCache is built (the library reads its knobs at cache creation / call time) and `--reps` proofs are timed
 (host clock around the synchronous call, L2 flushed in between, witness resident in HBM).
 
-  python tools/sched_probe.py --env B200_SCHED=0,1,2,3,4 [--constraints 3200000] [--precompute 16] [--reps 8]
+  python tools/knob_probe.py --env B200_MSM_QUAD=0 (knobs that are read once per process need one process per value) [--constraints 3200000] [--precompute 16] [--reps 8]
 """
 import argparse
 import os
