@@ -194,7 +194,7 @@ struct b200_zkey_cache {
   Fr *d_witness = nullptr, *d_vec = nullptr, *d_h = nullptr;
   uint8_t* d_results = nullptr; // 4 x G1 projective + 1 x G2 projective
   uint8_t* h_results = nullptr; // pinned
-  cudaStream_t s_copy = nullptr, s_g1 = nullptr, s_g2 = nullptr, s_g3 = nullptr, s_q = nullptr;
+  cudaStream_t s_copy = nullptr, s_g1 = nullptr, s_g2 = nullptr, s_g3 = nullptr, s_q = nullptr, s_h = nullptr;
   cudaEvent_t ev_start = nullptr, ev_h2d = nullptr, ev_r1cs = nullptr, ev_ntt = nullptr, ev_g1 = nullptr,
               ev_g2 = nullptr, ev_q = nullptr, ev_prev = nullptr, ev_b1 = nullptr, ev_free = nullptr;
   std::mutex mu;
@@ -388,7 +388,7 @@ namespace b200 {
     if (c->h_stage) cudaFreeHost(c->h_stage);
     if (c->ev_slice) cudaEventDestroy(c->ev_slice);
     if (c->ev_xch) cudaEventDestroy(c->ev_xch);
-    cudaStream_t ss[] = {c->s_copy, c->s_g1, c->s_g2, c->s_g3, c->s_q};
+    cudaStream_t ss[] = {c->s_copy, c->s_g1, c->s_g2, c->s_g3, c->s_q, c->s_h};
     for (auto s : ss)
       if (s) cudaStreamDestroy(s);
     cudaEvent_t es[] = {c->ev_start, c->ev_h2d, c->ev_r1cs, c->ev_ntt, c->ev_g1, c->ev_g2, c->ev_q, c->ev_prev, c->ev_b1, c->ev_free};
@@ -556,8 +556,16 @@ namespace b200 {
     CK(cudaStreamCreateWithPriority(&c->s_copy, cudaStreamNonBlocking, prio_hi));
     CK(cudaStreamCreateWithPriority(&c->s_q, cudaStreamNonBlocking, use_prio ? prio_hi : prio_lo));
     CK(cudaStreamCreateWithPriority(&c->s_g2, cudaStreamNonBlocking, use_prio && prio_hi + 1 <= prio_lo ? prio_hi + 1 : prio_lo));
-    CK(cudaStreamCreateWithPriority(&c->s_g1, cudaStreamNonBlocking, prio_lo));
-    CK(cudaStreamCreateWithPriority(&c->s_g3, cudaStreamNonBlocking, prio_lo));
+    // The H MSM runs LAST (lowest priority, own stream behind the transforms): every accumulation saturates the multiplier, so
+    // only the order of completion matters, and the bucket-reduction tail left exposed at the end of the proof should be
+    // the shortest one - H's single table (0.67 ms at 3200k) rather than the three fused G1 tables' (1.32 ms).
+    // B200_H_LAST=0 keeps H on the transforms' high-priority stream.
+    const char* hl = getenv("B200_H_LAST");
+    const bool h_last = use_prio && !(hl && hl[0] == '0') && prio_hi + 3 <= prio_lo - 1;
+    const int prio_g1 = h_last ? prio_hi + 3 : prio_lo;
+    CK(cudaStreamCreateWithPriority(&c->s_g1, cudaStreamNonBlocking, prio_g1));
+    CK(cudaStreamCreateWithPriority(&c->s_g3, cudaStreamNonBlocking, prio_g1));
+    if (h_last) CK(cudaStreamCreateWithPriority(&c->s_h, cudaStreamNonBlocking, prio_lo));
     for (cudaEvent_t* e : {&c->ev_prev, &c->ev_b1, &c->ev_free})
       CK(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
     for (cudaEvent_t* e : {&c->ev_start, &c->ev_h2d, &c->ev_r1cs, &c->ev_ntt, &c->ev_g1, &c->ev_g2, &c->ev_q})
@@ -896,11 +904,14 @@ namespace b200 {
     if (cnt) {
       B200_LAUNCH(quotient_combine_kernel, grid_for(cnt, 256, 8), 256, 0, c->s_q, a, b, cc, cnt, c->d_h + c->h_lo);
       cudaEventRecord(c->ev_ntt, c->s_q);
-      B200_TRY(msm_enqueue<Fq>(c->planH, c->d_h + c->h_lo, false, c->pH, result_slots(c).h, c->s_q));
+      cudaStream_t sh = c->s_h ? c->s_h : c->s_q;
+      if (sh != c->s_q) cudaStreamWaitEvent(sh, c->ev_ntt, 0);
+      B200_TRY(msm_enqueue<Fq>(c->planH, c->d_h + c->h_lo, false, c->pH, result_slots(c).h, sh));
+      cudaEventRecord(c->ev_q, sh);
     } else {
       cudaEventRecord(c->ev_ntt, c->s_q);
+      cudaEventRecord(c->ev_q, c->s_q);
     }
-    cudaEventRecord(c->ev_q, c->s_q);
     return ICICLE_SUCCESS;
   }
 
@@ -1262,8 +1273,8 @@ eIcicleError b200_groth16_commit_end(
   if (e == ICICLE_SUCCESS) e = enqueue_join(c);
   if (e == ICICLE_SUCCESS) e = commit_wait(c, out, tm);
   if (e != ICICLE_SUCCESS) { // drain whatever commit_begin enqueued so the next proof starts clean
-    for (cudaStream_t st : {c->s_copy, c->s_g1, c->s_g2, c->s_q})
-      cudaStreamSynchronize(st);
+    for (cudaStream_t st : {c->s_copy, c->s_g1, c->s_g2, c->s_q, c->s_h})
+      if (st) cudaStreamSynchronize(st);
     (void)cudaGetLastError();
   }
   c->in_flight = false;
@@ -1457,8 +1468,8 @@ eIcicleError b200_groth16_prove_sharded(
     if (rank == 0) be = compute_blind(c, r, s, bt); // host work overlapped with the GPU
   }
   // the one host wait of the proof (also drains a failed enqueue so the next proof starts clean)
-  for (cudaStream_t st : {c->s_q, c->s_g1, c->s_g2, c->s_copy})
-    if (cudaStreamSynchronize(st) != cudaSuccess && e == ICICLE_SUCCESS) e = ICICLE_SYNCHRONIZATION_FAILED;
+  for (cudaStream_t st : {c->s_q, c->s_h, c->s_g1, c->s_g2, c->s_copy})
+    if (st && cudaStreamSynchronize(st) != cudaSuccess && e == ICICLE_SUCCESS) e = ICICLE_SYNCHRONIZATION_FAILED;
   if (cudaGetLastError() != cudaSuccess && e == ICICLE_SUCCESS) e = (eIcicleError)ICICLE_UNKNOWN_FALLBACK;
   if (e != ICICLE_SUCCESS) return e;
   if (tm) {
