@@ -556,12 +556,12 @@ namespace b200 {
     CK(cudaStreamCreateWithPriority(&c->s_copy, cudaStreamNonBlocking, prio_hi));
     CK(cudaStreamCreateWithPriority(&c->s_q, cudaStreamNonBlocking, use_prio ? prio_hi : prio_lo));
     CK(cudaStreamCreateWithPriority(&c->s_g2, cudaStreamNonBlocking, use_prio && prio_hi + 1 <= prio_lo ? prio_hi + 1 : prio_lo));
-    // The H MSM runs LAST (lowest priority, own stream behind the transforms): every accumulation saturates the multiplier, so
-    // only the order of completion matters, and the bucket-reduction tail left exposed at the end of the proof should be
-    // the shortest one - H's single table (0.67 ms at 3200k) rather than the three fused G1 tables' (1.32 ms).
-    // B200_H_LAST=0 keeps H on the transforms' high-priority stream.
+    // B200_H_LAST=1 (experiment, off by default): the H MSM on its own lowest-priority stream behind the transforms, so that
+    // the bucket-reduction tail left exposed at the end of the proof is H's single table rather than the three fused G1
+    // tables'.  Measured 56.65 vs 56.10 ms at 3200k (profiles/r02_multi_gpu.md): H accumulating alone at the end costs
+    // more than the shorter tail saves.
     const char* hl = getenv("B200_H_LAST");
-    const bool h_last = use_prio && !(hl && hl[0] == '0') && prio_hi + 3 <= prio_lo - 1;
+    const bool h_last = use_prio && hl && hl[0] == '1' && prio_hi + 3 <= prio_lo - 1;
     const int prio_g1 = h_last ? prio_hi + 3 : prio_lo;
     CK(cudaStreamCreateWithPriority(&c->s_g1, cudaStreamNonBlocking, prio_g1));
     CK(cudaStreamCreateWithPriority(&c->s_g3, cudaStreamNonBlocking, prio_g1));
