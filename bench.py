@@ -373,7 +373,13 @@ def main():
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
 
     use_lib = world > 1 and args.split_quotient and args.exchange == "lib"
-    comm = pkg.multi_gpu.LibComm.from_torch(lib) if use_lib else None
+    comm = None
+    if use_lib:
+        try:
+            comm = pkg.multi_gpu.LibComm.from_torch(lib)
+        except RuntimeError as exc:  # no libnccl.so.2 for the library's dlopen: torch.distributed moves the slices instead
+            log(f"in-library communicator unavailable ({exc}); falling back to the torch.distributed exchange")
+            use_lib = False
     qx = pkg.multi_gpu.QuotientExchange(cache, torch.device("cuda", local)) if (world > 1 and args.split_quotient and not use_lib) else None
 
     def step(witness_ptr):
