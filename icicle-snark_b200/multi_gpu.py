@@ -112,17 +112,19 @@ class QuotientExchange:
 # ---- the library's own communicator (include/icicle_b200.h: b200_comm_*) ------------------------------------------
 class LibComm:
     """NCCL communicator owned by the C library: rank 0 draws the rendezvous token, `bcast` (any callable that returns
-    rank 0's 128 bytes on every rank - torch.distributed here, an MPI / TCP broadcast in another host) distributes it."""
+    rank 0's bytes on every rank - torch.distributed here, an MPI / TCP broadcast in another host) distributes it."""
 
     def __init__(self, lib, rank, world, bcast):
         self.lib, self.rank, self.world = lib, rank, world
         token = (C.c_uint8 * 128)()
+        status = 0
         if rank == 0:
-            rc = lib.dll.b200_comm_unique_id(token)
-            if rc != 0:
-                raise RuntimeError(f"b200_comm_unique_id failed: {rc} (no libnccl.so.2?)")
-        raw = bcast(bytes(token))
-        token = (C.c_uint8 * 128).from_buffer_copy(raw)
+            status = lib.dll.b200_comm_unique_id(token)
+        # the status travels with the token so that a failure on rank 0 (no libnccl.so.2) raises on every rank, not a hang
+        raw = bcast(bytes([status & 0xFF]) + bytes(token))
+        if raw[0] != 0:
+            raise RuntimeError(f"b200_comm_unique_id failed on rank 0: {raw[0]} (no libnccl.so.2?)")
+        token = (C.c_uint8 * 128).from_buffer_copy(raw[1:129])
         h = C.c_void_p()
         rc = lib.dll.b200_comm_create(token, C.c_int(rank), C.c_int(world), C.byref(h))
         if rc != 0:

@@ -164,3 +164,42 @@ def test_line_plan_partitions_and_balances(lib, monkeypatch):
     assert lib.dll.b200_shard_plan(C.c_uint32(10), C.c_uint32(16), 4, 4, 1, C.c_double(0), lo, hi) != 0
     assert lib.dll.b200_shard_plan(C.c_uint32(10), C.c_uint32(16), 0, 4, 2, C.c_double(0), lo, hi) != 0
     assert lib.dll.b200_shard_plan(C.c_uint32(10), C.c_uint32(16), 0, 4, 1, C.c_double(0), None, hi) != 0
+
+
+def _comm_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import conftest  # noqa: F401
+    import torch.distributed as dist
+    import icicle_snark_b200 as pkg
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    try:
+        lib = pkg.lib()
+        try:
+            pkg.multi_gpu.LibComm.from_torch(lib)
+            q.put((rank, "created"))
+        except RuntimeError as exc:
+            q.put((rank, "error: " + str(exc)[:60]))
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_comm_setup_fails_on_every_rank_without_a_gpu():
+    """LibComm's rendezvous (rank 0 draws the token, status + token broadcast by the host's own channel - gloo here): without
+    a CUDA device the library cannot join a communicator, and that must surface as an error on EVERY rank, never as a hang
+    of the ranks that wait for rank 0 (bench.py then falls back to the torch.distributed exchange)."""
+    from conftest import HAS_GPU
+    if HAS_GPU:
+        pytest.skip("CPU-only behaviour")
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_comm_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    got = dict(q.get(timeout=5) for _ in range(2))
+    assert set(got) == {0, 1} and all(v.startswith("error") for v in got.values()), got
