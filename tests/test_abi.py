@@ -74,3 +74,18 @@ def test_header_is_plain_c_and_links(tmp_path):
                     f"-Wl,-rpath,{libdir}"], check=True)
     out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()
     assert out[:5] == ["40", "64", "32", "256", "384"] and "sm_100a" in out
+
+
+def test_plain_c_multi_gpu_host_example_compiles_and_links(tmp_path):
+    """examples/multi_gpu_host.c: the multi-GPU data plane driven from plain C (fork + pipes for the token), i.e. what a
+    Rust / Go / Java host does through its FFI.  Must compile as strict C99 against the public header alone and link against
+    the library; without arguments it prints its usage (running it needs GPUs)."""
+    import subprocess
+    src = os.path.join(ROOT, "examples", "multi_gpu_host.c")
+    inc = os.path.join(ROOT, "include")
+    libdir = os.path.dirname(pkg.LIB_PATH)
+    exe = tmp_path / "multi_gpu_host"
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", inc, src, "-o", str(exe), "-L", libdir,
+                    "-licicle_b200", f"-Wl,-rpath,{libdir}"], check=True)
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 2 and "usage" in r.stderr
