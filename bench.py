@@ -12,9 +12,10 @@ snarkjs/circom are unavailable offline) with fixed NON-trivial blinding factors 
 witness already in HBM (device pointer), timed around the synchronous C-ABI call between device synchronisations
 (barrier + max over ranks); `e2e` = the same call with the witness in pinned HOST memory and the proof read back to the
 host, copies inside the timed region.  The last timed proof is verified outside the timed region with the library's
-own pairing check AND the reference's (`oracle/_ref` bn254_pairing): "verified".  N > 1 (torchrun): every rank holds a
-contiguous shard of the five base-point sets; partial sums are gathered over NCCL; rank 0 folds + blinds (strong
-scaling: the job is one proof).
+own pairing check AND the reference's (`oracle/_ref` bn254_pairing): "verified".  N > 1 (torchrun): every rank holds its
+pieces of the five base-point tables (b200_shard_plan) and calls b200_groth16_prove_sharded - quotient slices, the witness
+all-gather and the 576-byte gather of partial sums travel over NCCL inside the library; rank 0 folds + blinds (strong
+scaling: the job is one proof).  `extras.sweep` carries the standalone MSM / NTT sweeps at the same N.
 `roofline` describes the dominant kernel - the G1 bucket accumulation launch the proof really issues (three tables sharing
 one sort), timed ISOLATED in an extra profiled proof after the timed region - against the integer multiply pipe, whose
 peak is measured in the same run (research/pipes2.cu).  `cpu_baseline`: the reference CPU library on this box's host
